@@ -1,0 +1,148 @@
+/* ssb200.h -- C ABI of libssb200.so: the B200 (sm_100a) implementation of the
+ * SoundSpaces per-step audio observation (binaural RIR (*) source -> waveform ->
+ * log-magnitude spectrogram).
+ *
+ * The reference is 100 % Python and has no FFI of its own for this path; the
+ * entry points below are what a ctypes binding inside the reference would bind
+ * in place of the following reference code (paths relative to the upstream
+ * repository, see INTEGRATION.md for the binding stub):
+ *
+ *   ssb_source_windows      <- the source-side half of scipy.signal.fftconvolve as
+ *                              called at soundspaces/simulator.py:630,638,645,661 and
+ *                              soundspaces/continuous_simulator.py:436,449 (one clip,
+ *                              cached per (sound, sample offset) like
+ *                              simulator.py:595-600 caches the decoded clip)
+ *   ssb_convolve_batch      <- SoundSpacesSim._compute_audiogoal,
+ *                              soundspaces/simulator.py:608-666 (all branches) and
+ *                              ContinuousSoundSpacesSim._convolve_with_rir,
+ *                              soundspaces/continuous_simulator.py:428-456
+ *   ssb_crossfade_batch     <- crossfade(), soundspaces/continuous_simulator.py:47-53
+ *   ssb_spectrogram_batch   <- SpectrogramSensor.compute_spectrogram,
+ *                              soundspaces/tasks/nav.py:86-100
+ *   ssb_render_batch        <- get_current_spectrogram_observation,
+ *                              soundspaces/simulator.py:690-701 for a batch of envs
+ *   ssb_render_batch_host   <- the same with host buffers (what the per-env numpy API
+ *                              of the reference hands over), copies included
+ *   ssb_pcm16_decode/encode <- int16 <-> float32 PCM (librosa.load decode used at
+ *                              simulator.py:597; np.int16(audio*32767) at
+ *                              scripts/interactive_demo.py:110)
+ *
+ * Conventions: every function returns 0 on success or a negative SSB_E* code and
+ * never throws; ssb_last_error(ctx) describes the last failure.  All pointers
+ * named d_* are device pointers on the context's device; h_* are host pointers
+ * (pinned for asynchronous copies).  Work is enqueued on the caller's stream
+ * (a cudaStream_t passed as void*; NULL = legacy default stream) and is
+ * asynchronous; a context is not thread-safe.  No torch types cross this ABI.
+ */
+#ifndef SSB200_H
+#define SSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_OK 0
+#define SSB_E_INVALID_ARG (-1)
+#define SSB_E_CUDA (-2)
+#define SSB_E_OOM (-3)
+#define SSB_E_SHAPE (-4)
+
+#define SSB_FLAG_SILENT 1u      /* simulator.py:610-612: exact zeros */
+
+#define SSB_PAD_REFLECT 0       /* librosa < 0.10 default */
+#define SSB_PAD_CONSTANT 1      /* librosa >= 0.10 default */
+
+#define SSB_N_FFT 512           /* nav.py:89-91 */
+#define SSB_HOP 160
+#define SSB_WIN 400
+#define SSB_POOL 4              /* nav.py:93 */
+#define SSB_SPEC_ROWS 65        /* ceil(257 / 4) */
+
+typedef struct ssb_ctx ssb_ctx;
+
+/* One convolution term: out[m] += sum_{k < rir_taps} rir[k] * src_ext[m0 + m - k].
+ * The source enters through its overlap-save window spectra (ssb_source_windows). */
+typedef struct {
+    int64_t rir_offset; /* first tap of the (taps, 2) float32 interleaved RIR, in taps from d_rir_bank */
+    int64_t x_offset;   /* first element (float2 units) of the window spectra, from d_xpool */
+    int32_t rir_taps;   /* taps to use = min(file taps, m0 + out_samples); 0 => term contributes nothing
+                           (zero-RIR fallback simulator.py:617-624, or unused distractor slot) */
+    int32_t x_nw;       /* number of windows stored at x_offset */
+    int32_t x_wofs;     /* stored window j holds overlap-save block index j - x_wofs */
+    int32_t reserved;
+} ssb_conv_term;
+
+typedef struct {
+    ssb_conv_term term[2]; /* [0] the goal sound, [1] the distractor (simulator.py:649-664) */
+    int32_t out_samples;   /* valid samples; [out_samples, sr) is zero (continuous_simulator.py:454) */
+    uint32_t flags;        /* SSB_FLAG_* */
+} ssb_req;
+
+typedef struct {
+    int32_t log2n;      /* FFT size of the overlap-save blocks: 12, 13 or 14 */
+    int32_t block;      /* P = 2^log2n / 2 output samples per block */
+    int32_t sr;         /* samples per output row (RIR_SAMPLING_RATE) */
+    int32_t n_blocks;   /* ceil(sr / P) */
+    int32_t max_parts;  /* RIR partitions the scratch is sized for */
+    int32_t n_terms;    /* 1 or 2 */
+    int64_t h_elems_per_env; /* float2 elements of RIR-spectrum scratch per env */
+} ssb_plan;
+
+int ssb_version(void);
+int ssb_create(int device, ssb_ctx** out);
+void ssb_destroy(ssb_ctx* ctx);
+const char* ssb_last_error(const ssb_ctx* ctx);
+/* kernels launched by this context since creation (for bench.py's gpu_launches) */
+int64_t ssb_launch_count(const ssb_ctx* ctx);
+
+/* Fill a plan.  log2n = 0 picks the default (13). */
+int ssb_make_plan(ssb_ctx* ctx, int sr, int max_taps, int n_terms, int log2n, ssb_plan* plan);
+
+/* spectrogram geometry: frames = 1 + sr/160, cols = ceil(frames/4) */
+int ssb_spec_cols(int sr);
+
+/* Overlap-save window spectra of one mono clip.  Window j (0 <= j < nw) covers source
+ * samples [m0 + (j - wofs - 1) * P, m0 + (j - wofs + 1) * P); samples < 0 read as 0, samples >= S
+ * read as src[n - S] when wrap != 0 (continuous_simulator.py:443-445) else 0.
+ * d_x receives nw * 2^log2n float2. */
+int ssb_source_windows(ssb_ctx* ctx, const ssb_plan* plan, const float* d_src, int S, int64_t m0, int wrap,
+                       int nw, int wofs, void* d_x, void* stream);
+
+/* Convolve a batch: d_wave[env][ear][n], row stride wave_stride floats (>= sr), ear 0 = left.
+ * d_hscratch: B * plan->h_elems_per_env float2. */
+int ssb_convolve_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs,
+                       const float* d_rir_bank, const void* d_xpool, void* d_hscratch,
+                       float* d_wave, int64_t wave_stride, void* stream);
+
+/* out[env][:, :n+1] = a*w1 + b*w2 over the first n+1 = int(0.05*sr)+1 samples, rest = b; in place on b. */
+int ssb_crossfade_batch(ssb_ctx* ctx, int B, const float* d_prev, float* d_cur, int sr,
+                        int64_t wave_stride, const uint8_t* d_enable, void* stream);
+
+/* d_spec[env][65][cols][2] = log1p(mean4x4(|STFT(d_wave[env][ear])|)) */
+int ssb_spectrogram_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr,
+                          int pad_mode, float* d_spec, void* stream);
+
+/* convolve + spectrogram.  d_wave is required (it is the intermediate). */
+int ssb_render_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs,
+                     const float* d_rir_bank, const void* d_xpool, void* d_hscratch,
+                     float* d_wave, int64_t wave_stride, int pad_mode, float* d_spec, void* stream);
+
+/* Host-buffer entry: copies h_rir (rir_bytes) and h_reqs to the device staging buffers the
+ * caller provides, renders, and copies the spectrogram (and the waveform when h_wave != NULL,
+ * densely packed [B][2][sr]) back to the host.  All on `stream`; the caller synchronises. */
+int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* h_reqs,
+                          const float* h_rir, int64_t rir_bytes, float* d_rir_staging, ssb_req* d_reqs_staging,
+                          const void* d_xpool, void* d_hscratch, float* d_wave, int64_t wave_stride,
+                          int pad_mode, float* d_spec, float* h_spec, float* h_wave, void* stream);
+
+/* PCM helpers.  decode: float32(x) / 32768 (exact).  encode mode 0: round(x*32768) saturated;
+ * mode 1: trunc(x*32767) saturated (interactive_demo.py:110). */
+int ssb_pcm16_decode(ssb_ctx* ctx, const int16_t* d_in, int64_t n, float* d_out, void* stream);
+int ssb_pcm16_encode(ssb_ctx* ctx, const float* d_in, int64_t n, int mode, int16_t* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSB200_H */

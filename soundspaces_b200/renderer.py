@@ -1,0 +1,349 @@
+"""Batched device-side audio renderer: the host half of the B200 audio path.
+
+Owns the device-resident RIR bank, the source clips with their
+cached overlap-save window spectra (the per-sound cache of
+``soundspaces/simulator.py:595-600`` moved to the device), and the scratch the
+kernels need.  One ``render()`` call replaces, for a whole batch of envs, one
+cache-missing ``get_current_spectrogram_observation`` each
+(``soundspaces/simulator.py:690-701`` -> ``_compute_audiogoal`` ``:608-666`` ->
+``SpectrogramSensor.compute_spectrogram`` ``soundspaces/tasks/nav.py:86-100``).
+
+PyTorch is used for device memory and streams only; all arithmetic runs in
+``libssb200.so`` (hand-written sm_100a CUDA) through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PAD_MODES, REQ_DTYPE, SSB_FLAG_SILENT
+
+N_FFT, HOP, WIN, POOL, SPEC_ROWS = 512, 160, 400, 4, 65
+
+
+def spectrogram_shape(sr: int):
+    """(65, ceil((1 + sr//160)/4), 2): (65, 26, 2) @16 kHz, (65, 69, 2) @44.1 kHz."""
+    frames = 1 + sr // HOP
+    return (SPEC_ROWS, -(-frames // POOL), 2)
+
+
+@dataclass
+class AudioRequest:
+    """One env-step.  ``out[m] = sum_k rir[k] * src[offset + m - k]`` for m < out_samples.
+
+    offset: 0 for 1-s clips (simulator.py:629-632); ``index * sr`` for multi-second clips
+    (simulator.py:634-647, both the early and the ``valid`` branch); the running
+    ``_current_sample_index`` for the continuous simulator (continuous_simulator.py:428-456).
+    """
+    rir: int                       # id in the RIR bank; -1 => unreadable/empty file => zero RIR (simulator.py:617-624)
+    source: int                    # id of the source clip
+    offset: int = 0
+    out_samples: Optional[int] = None      # default sr; int(sr*STEP_TIME) for the continuous simulator
+    wrap: bool = False             # continuous_simulator.py:443-445 wrap-around of the clip
+    silent: bool = False           # simulator.py:610-612
+    distractor_rir: Optional[int] = None   # simulator.py:649-664
+    distractor_source: Optional[int] = None
+
+
+@dataclass
+class PreparedBatch:
+    n: int
+    reqs_host: np.ndarray
+    reqs_dev: torch.Tensor
+
+
+def _dev_index(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("BatchedAudioRenderer needs a CUDA device; there is no CPU fallback")
+    return torch.cuda.current_device() if device.index is None else device.index
+
+
+class BatchedAudioRenderer:
+    def __init__(self, sr: int, max_taps: int, device="cuda:0", n_terms: int = 1, log2n: int = 0,
+                 pad_mode: str = "reflect", xpool_bytes: int = 512 << 20):
+        self.sr = int(sr)
+        self.device = torch.device("cuda", _dev_index(device))
+        self.pad_mode = PAD_MODES[pad_mode]
+        torch.cuda.set_device(self.device)
+        self.ctx = _lib.Context(self.device.index)
+        self.lib = self.ctx.lib
+        self.max_taps = int(max_taps)
+        self.plan = self.ctx.make_plan(self.sr, self.max_taps, n_terms, log2n)
+        self.N = 1 << self.plan.log2n
+        self.P = self.plan.block
+        self.spec_shape = spectrogram_shape(self.sr)
+        assert self.spec_shape[1] == self.lib.ssb_spec_cols(self.sr)
+        # RIR bank: (total_taps, 2) float32, interleaved ears == one complex signal
+        self._bank = torch.zeros((1, 2), dtype=torch.float32, device=self.device)
+        self._bank_used = 0
+        self._rir_off: list[int] = []
+        self._rir_len: list[int] = []
+        # sources + window-spectra pool
+        self._sources: list[torch.Tensor] = []
+        self._xpool = torch.empty(max(xpool_bytes // 8, 64 * self.N) * 2, dtype=torch.float32, device=self.device)
+        self._xpool_used = 0                  # float2 elements
+        self._xcache: dict = {}
+        self._hscratch = None
+        self._wave = None
+        self._prev_wave = None
+
+    # ------------------------------------------------------------------ banks
+    def add_rirs(self, rirs: Sequence) -> list:
+        """Append RIRs ((L, 2) float32 arrays / tensors; None or empty => zero-RIR fallback)."""
+        ids, chunks, total = [], [], 0
+        for r in rirs:
+            if r is None or len(r) == 0:
+                self._rir_off.append(0)
+                self._rir_len.append(0)
+            else:
+                t = torch.as_tensor(r, dtype=torch.float32)
+                if t.ndim != 2 or t.shape[1] != 2:
+                    raise ValueError(f"RIR must be (L, 2), got {tuple(t.shape)}")
+                self._rir_off.append(self._bank_used + total)
+                self._rir_len.append(t.shape[0])
+                chunks.append(t)
+                total += t.shape[0]
+            ids.append(len(self._rir_off) - 1)
+        if total:
+            need = self._bank_used + total
+            if need > self._bank.shape[0]:
+                grown = torch.empty((max(need, 2 * self._bank.shape[0]), 2), dtype=torch.float32, device=self.device)
+                grown[: self._bank_used] = self._bank[: self._bank_used]
+                self._bank = grown
+            host = torch.cat([c.cpu() if c.is_cuda else c for c in chunks]) if not all(c.is_cuda for c in chunks) \
+                else torch.cat(chunks)
+            self._bank[self._bank_used: need].copy_(host, non_blocking=True)
+            self._bank_used = need
+        return ids
+
+    def set_dense_rir_bank(self, rirs: torch.Tensor) -> list:
+        """Adopt an already device-resident (n, L, 2) float32 tensor as the bank (no copy)."""
+        if not (rirs.is_cuda and rirs.dtype == torch.float32 and rirs.is_contiguous() and rirs.ndim == 3
+                and rirs.shape[2] == 2):
+            raise ValueError("expected a contiguous CUDA float32 (n, L, 2) tensor")
+        n, L, _ = rirs.shape
+        self._bank = rirs.view(n * L, 2)
+        self._bank_used = n * L
+        self._rir_off = [i * L for i in range(n)]
+        self._rir_len = [L] * n
+        return list(range(n))
+
+    def add_source(self, samples) -> int:
+        """Register a mono clip already at ``sr`` (float32).  Returns its id."""
+        t = torch.as_tensor(samples, dtype=torch.float32).reshape(-1).to(self.device).contiguous()
+        if t.numel() == 0:
+            raise ValueError("empty source clip")
+        self._sources.append(t)
+        return len(self._sources) - 1
+
+    def add_source_pcm16(self, pcm) -> int:
+        """Register an int16 clip; decoded on the device as float32(x)/32768 (bit-exact
+        with the soundfile decode behind ``librosa.load``, simulator.py:597)."""
+        p = torch.as_tensor(np.ascontiguousarray(pcm, dtype=np.int16)).to(self.device)
+        out = torch.empty(p.numel(), dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.ssb_pcm16_decode(self.ctx.handle, p.data_ptr(), p.numel(), out.data_ptr(),
+                                                 self._stream()), "ssb_pcm16_decode")
+        self._sources.append(out)
+        return len(self._sources) - 1
+
+    def encode_pcm16(self, wave: torch.Tensor, mode: str = "round") -> torch.Tensor:
+        w = wave.contiguous()
+        out = torch.empty(w.shape, dtype=torch.int16, device=self.device)
+        self.ctx.check(self.lib.ssb_pcm16_encode(self.ctx.handle, w.data_ptr(), w.numel(),
+                                                 {"round": 0, "demo": 1}[mode], out.data_ptr(), self._stream()),
+                       "ssb_pcm16_encode")
+        return out
+
+    # ---------------------------------------------------------------- helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _windows(self, source: int, offset: int, wrap: bool, out_samples: int):
+        """Cached overlap-save window spectra of (clip, offset).  Returns (x_offset, nw, wofs)."""
+        P = self.P
+        nblk = -(-out_samples // P)
+        wofs = min(self.plan.max_parts - 1, -(-offset // P))
+        key = (source, offset, bool(wrap), nblk, wofs)
+        hit = self._xcache.get(key)
+        if hit is not None:
+            return hit
+        nw = nblk + wofs
+        need = nw * self.N
+        if self._xpool_used + need > self._xpool.numel() // 2:
+            if need > self._xpool.numel() // 2:
+                raise RuntimeError("window-spectra pool too small for one clip; raise xpool_bytes")
+            # simplest policy: drop every cached set (they are recomputed on demand)
+            torch.cuda.current_stream(self.device).synchronize()
+            self._xcache.clear()
+            self._xpool_used = 0
+        x_off = self._xpool_used
+        src = self._sources[source]
+        self.ctx.check(self.lib.ssb_source_windows(
+            self.ctx.handle, C.byref(self.plan), src.data_ptr(), src.numel(), int(offset), int(bool(wrap)),
+            nw, wofs, self._xpool.data_ptr() + 8 * x_off, self._stream()), "ssb_source_windows")
+        self._xpool_used += need
+        self._xcache[key] = (x_off, nw, wofs)
+        return self._xcache[key]
+
+    def _fill_term(self, term, rir_id, source, offset, wrap, out_samples):
+        if rir_id is None or rir_id < 0 or self._rir_len[rir_id] == 0:
+            term["rir_taps"] = 0
+            return
+        taps = min(self._rir_len[rir_id], offset + out_samples, self.plan.max_parts * self.P)
+        if self._rir_len[rir_id] > self.max_taps and offset + out_samples > self.max_taps:
+            raise ValueError(f"RIR {rir_id} has {self._rir_len[rir_id]} taps > max_taps={self.max_taps}")
+        x_off, nw, wofs = self._windows(source, offset, wrap, out_samples)
+        term["rir_offset"] = self._rir_off[rir_id]
+        term["x_offset"] = x_off
+        term["rir_taps"] = taps
+        term["x_nw"] = nw
+        term["x_wofs"] = wofs
+
+    # ----------------------------------------------------------------- render
+    def prepare(self, requests: Sequence[AudioRequest]) -> PreparedBatch:
+        n = len(requests)
+        reqs = np.zeros(n, dtype=REQ_DTYPE)
+        for i, r in enumerate(requests):
+            out_samples = self.sr if r.out_samples is None else int(r.out_samples)
+            if not 0 < out_samples <= self.sr:
+                raise ValueError("out_samples must be in (0, sr]")
+            reqs[i]["out_samples"] = out_samples
+            if r.silent:
+                reqs[i]["flags"] = SSB_FLAG_SILENT
+                continue
+            self._fill_term(reqs[i]["term"][0], r.rir, r.source, int(r.offset), r.wrap, out_samples)
+            if r.distractor_source is not None:
+                if self.plan.n_terms < 2:
+                    raise ValueError("renderer was created with n_terms=1; distractors need n_terms=2")
+                # the whole distractor clip is convolved in full mode and cut to [:sr] (simulator.py:661-664)
+                self._fill_term(reqs[i]["term"][1], r.distractor_rir, r.distractor_source, 0, False, out_samples)
+        dev = torch.from_numpy(reqs.view(np.uint8).reshape(-1)).to(self.device, non_blocking=False)
+        return PreparedBatch(n, reqs, dev)
+
+    def _scratch(self, n):
+        h_elems = n * self.plan.h_elems_per_env
+        if self._hscratch is None or self._hscratch.numel() < 2 * h_elems:
+            self._hscratch = torch.empty(2 * h_elems, dtype=torch.float32, device=self.device)
+        if self._wave is None or self._wave.shape[0] < n:
+            self._wave = torch.empty((n, 2, self.sr), dtype=torch.float32, device=self.device)
+        return self._hscratch, self._wave[:n]
+
+    def execute(self, batch: PreparedBatch, want_wave: bool = False, out: Optional[torch.Tensor] = None):
+        """Run convolution + spectrogram for a prepared batch on the current stream.
+        Returns spec (n, 65, T', 2) [, wave (n, 2, sr)] as CUDA tensors.  The waveform buffer is
+        owned by the renderer and overwritten by the next call (clone to keep)."""
+        n = batch.n
+        spec = out if out is not None else torch.empty((n,) + self.spec_shape, dtype=torch.float32, device=self.device)
+        if n == 0:
+            return (spec, self._scratch(0)[1]) if want_wave else spec
+        if not (spec.is_cuda and spec.is_contiguous() and spec.shape == (n,) + self.spec_shape):
+            raise ValueError("bad output tensor")
+        hs, wave = self._scratch(n)
+        self.ctx.check(self.lib.ssb_render_batch(
+            self.ctx.handle, C.byref(self.plan), n, batch.reqs_dev.data_ptr(), self._bank.data_ptr(),
+            self._xpool.data_ptr(), hs.data_ptr(), wave.data_ptr(), self.sr, self.pad_mode, spec.data_ptr(),
+            self._stream()), "ssb_render_batch")
+        return (spec, wave) if want_wave else spec
+
+    def render(self, requests: Sequence[AudioRequest], want_wave: bool = False):
+        return self.execute(self.prepare(requests), want_wave=want_wave)
+
+    def convolve(self, requests: Sequence[AudioRequest]) -> torch.Tensor:
+        """Waveforms only: (n, 2, sr) -- ``get_current_audiogoal_observation`` for a batch."""
+        batch = self.prepare(requests)
+        hs, wave = self._scratch(batch.n)
+        if batch.n:
+            self.ctx.check(self.lib.ssb_convolve_batch(
+                self.ctx.handle, C.byref(self.plan), batch.n, batch.reqs_dev.data_ptr(), self._bank.data_ptr(),
+                self._xpool.data_ptr(), hs.data_ptr(), wave.data_ptr(), self.sr, self._stream()), "ssb_convolve_batch")
+        return wave
+
+    def render_crossfade(self, cur: Sequence[AudioRequest], prev: Sequence[Optional[AudioRequest]],
+                         want_wave: bool = False):
+        """Continuous simulator with CROSSFADE (continuous_simulator.py:422-424): render with the
+        previous RIR and with the current one, blend the first int(0.05*sr)+1 samples."""
+        n = len(cur)
+        enable = torch.tensor([p is not None for p in prev], dtype=torch.uint8, device=self.device)
+        prev_reqs = [p if p is not None else c for p, c in zip(prev, cur)]
+        w_prev = self.convolve(prev_reqs)
+        if self._prev_wave is None or self._prev_wave.shape[0] < n:
+            self._prev_wave = torch.empty((n, 2, self.sr), dtype=torch.float32, device=self.device)
+        pw = self._prev_wave[:n]
+        pw.copy_(w_prev)
+        wave = self.convolve(cur)
+        self.ctx.check(self.lib.ssb_crossfade_batch(self.ctx.handle, n, pw.data_ptr(), wave.data_ptr(), self.sr,
+                                                    self.sr, enable.data_ptr(), self._stream()), "ssb_crossfade_batch")
+        spec = self.spectrogram(wave)
+        return (spec, wave) if want_wave else spec
+
+    def spectrogram(self, wave: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``SpectrogramSensor.compute_spectrogram`` (nav.py:86-100) for a (n, 2, sr) CUDA batch."""
+        if wave.ndim == 2:
+            wave = wave[None]
+        if not (wave.is_cuda and wave.dtype == torch.float32 and wave.shape[1] == 2 and wave.shape[2] == self.sr):
+            raise ValueError(f"expected CUDA float32 (n, 2, {self.sr})")
+        wave = wave.contiguous()
+        n = wave.shape[0]
+        spec = out if out is not None else torch.empty((n,) + self.spec_shape, dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.ssb_spectrogram_batch(self.ctx.handle, n, wave.data_ptr(), self.sr, self.sr,
+                                                      self.pad_mode, spec.data_ptr(), self._stream()),
+                       "ssb_spectrogram_batch")
+        return spec
+
+    # --------------------------------------------------------- host-buffer path
+    def make_host_session(self, n: int, taps: int, want_wave: bool = False):
+        """Pinned host buffers + device staging for ``render_host`` (the e2e path)."""
+        return HostSession(self, n, taps, want_wave)
+
+
+class HostSession:
+    """End-to-end entry with HOST buffers: per step the (n, taps, 2) RIRs are copied from pinned
+    host memory, rendered, and the spectrograms (optionally waveforms) are copied back --
+    what the reference's per-env numpy API hands over and gets back."""
+
+    def __init__(self, r: BatchedAudioRenderer, n: int, taps: int, want_wave: bool):
+        self.r, self.n, self.taps = r, n, taps
+        self.h_rir = torch.empty((n, taps, 2), dtype=torch.float32).pin_memory()
+        self.h_spec = torch.empty((n,) + r.spec_shape, dtype=torch.float32).pin_memory()
+        self.h_wave = torch.empty((n, 2, r.sr), dtype=torch.float32).pin_memory() if want_wave else None
+        self.h_reqs = torch.empty(n * REQ_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        self.d_rir = torch.empty((n, taps, 2), dtype=torch.float32, device=r.device)
+        self.d_reqs = torch.empty(n * REQ_DTYPE.itemsize, dtype=torch.uint8, device=r.device)
+        self.d_spec = torch.empty((n,) + r.spec_shape, dtype=torch.float32, device=r.device)
+        self.h2d_bytes = self.h_rir.numel() * 4 + self.h_reqs.numel()
+        self.d2h_bytes = self.h_spec.numel() * 4 + (self.h_wave.numel() * 4 if want_wave else 0)
+
+    def set_requests(self, source: int, silent=None, taps=None):
+        """All envs play ``source`` through their own RIR row (the 1-s clip branch)."""
+        r = self.r
+        reqs = np.zeros(self.n, dtype=REQ_DTYPE)
+        for i in range(self.n):
+            reqs[i]["out_samples"] = r.sr
+            if silent is not None and silent[i]:
+                reqs[i]["flags"] = SSB_FLAG_SILENT
+                continue
+            L = self.taps if taps is None else int(taps[i])
+            if L == 0:
+                continue
+            x_off, nw, wofs = r._windows(source, 0, False, r.sr)
+            t = reqs[i]["term"][0]
+            t["rir_offset"], t["x_offset"], t["rir_taps"] = i * self.taps, x_off, min(L, r.sr, r.plan.max_parts * r.P)
+            t["x_nw"], t["x_wofs"] = nw, wofs
+        self.h_reqs.numpy()[:] = reqs.view(np.uint8).reshape(-1)
+
+    def run(self):
+        """Enqueue H2D + kernels + D2H on the current stream (asynchronous)."""
+        r = self.r
+        hs, wave = r._scratch(self.n)
+        r.ctx.check(r.lib.ssb_render_batch_host(
+            r.ctx.handle, C.byref(r.plan), self.n, self.h_reqs.data_ptr(), self.h_rir.data_ptr(),
+            self.h_rir.numel() * 4, self.d_rir.data_ptr(), self.d_reqs.data_ptr(), r._xpool.data_ptr(),
+            hs.data_ptr(), wave.data_ptr(), r.sr, r.pad_mode, self.d_spec.data_ptr(), self.h_spec.data_ptr(),
+            self.h_wave.data_ptr() if self.h_wave is not None else None, r._stream()), "ssb_render_batch_host")
+        return self.h_spec
