@@ -97,6 +97,17 @@ const char* ssb_last_error(const ssb_ctx* ctx);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 int64_t ssb_launch_count(const ssb_ctx* ctx);
 
+/* Optional per-kernel timing for bench.py's roofline: when enabled every kernel launch is
+ * bracketed by CUDA events on the launching stream.  ssb_get_kernel_timing synchronises, writes
+ * the summed milliseconds and launch counts per kernel (index SSB_K_*) and clears the record. */
+#define SSB_K_FWD_RIR 0
+#define SSB_K_MAC_IFFT 1
+#define SSB_K_SPECTROGRAM 2
+#define SSB_K_FWD_SRC 3
+#define SSB_N_KERNELS 4
+int ssb_set_kernel_timing(ssb_ctx* ctx, int enable);
+int ssb_get_kernel_timing(ssb_ctx* ctx, double* ms_sum /*[SSB_N_KERNELS]*/, int64_t* counts /*[SSB_N_KERNELS]*/);
+
 /* Fill a plan.  log2n = 0 picks the default (13). */
 int ssb_make_plan(ssb_ctx* ctx, int sr, int max_taps, int n_terms, int log2n, ssb_plan* plan);
 

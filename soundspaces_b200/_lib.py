@@ -43,6 +43,8 @@ EXPORTS = {
     "ssb_destroy": (None, [C.c_void_p]),
     "ssb_last_error": (C.c_char_p, [C.c_void_p]),
     "ssb_launch_count": (C.c_int64, [C.c_void_p]),
+    "ssb_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssb_get_kernel_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ssb_make_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Plan)]),
     "ssb_spec_cols": (C.c_int, [C.c_int]),
     "ssb_source_windows": (C.c_int, [C.c_void_p, C.POINTER(Plan), C.c_void_p, C.c_int, C.c_int64, C.c_int,
@@ -122,6 +124,18 @@ class Context:
         plan = Plan()
         self.check(self.lib.ssb_make_plan(self.handle, sr, max_taps, n_terms, log2n, C.byref(plan)), "ssb_make_plan")
         return plan
+
+    KERNEL_NAMES = ("fwd_rir_kernel", "mac_ifft_kernel", "spectrogram_kernel", "fwd_src_kernel")
+
+    def set_kernel_timing(self, enable):
+        self.check(self.lib.ssb_set_kernel_timing(self.handle, int(bool(enable))), "ssb_set_kernel_timing")
+
+    def get_kernel_timing(self):
+        """{kernel: (summed ms, launches)} since the last call (synchronises)."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        self.check(self.lib.ssb_get_kernel_timing(self.handle, ms, cnt), "ssb_get_kernel_timing")
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(self.KERNEL_NAMES)}
 
     @property
     def launch_count(self):

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "../../include/ssb200.h"
 #include "fft16.cuh"
@@ -22,12 +23,18 @@ using namespace ssb;
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+enum { K_FWD_RIR = 0, K_MAC_IFFT = 1, K_SPECTROGRAM = 2, K_FWD_SRC = 3, K_COUNT = SSB_N_KERNELS };
+struct TimedLaunch { int kernel; cudaEvent_t a, b; };
+
 struct ssb_ctx {
     int device;
     int sm_count;
     float2* tw[16];      // twiddle tables by log2n (device)
     float* window;       // 512-float centre-padded periodic Hann(400)
     int64_t launches;
+    // optional per-kernel CUDA-event timing (bench.py roofline); see ssb_set_kernel_timing
+    int timing;
+    std::vector<TimedLaunch>* timed;
     char err[512];
 };
 
@@ -46,6 +53,22 @@ struct ssb_ctx {
     } while (0)
 
 static const int kSupportedLog2[] = {9, 12, 13, 14};
+
+struct LaunchTimer {          // records an event pair around one kernel launch when timing is on
+    ssb_ctx* ctx; cudaStream_t st; TimedLaunch tl; bool on;
+    LaunchTimer(ssb_ctx* c, int kernel, cudaStream_t s) : ctx(c), st(s), on(c->timing && c->timed) {
+        ctx->launches += 1;
+        if (!on) return;
+        tl.kernel = kernel;
+        if (cudaEventCreate(&tl.a) != cudaSuccess || cudaEventCreate(&tl.b) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(tl.a, st);
+    }
+    ~LaunchTimer() {
+        if (!on) return;
+        cudaEventRecord(tl.b, st);
+        ctx->timed->push_back(tl);
+    }
+};
 
 // ---------------------------------------------------------------------------
 // forward FFT kernels
@@ -338,6 +361,7 @@ extern "C" int ssb_create(int device, ssb_ctx** out) {
     if (!ctx) return SSB_E_OOM;
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
+    ctx->timed = new (std::nothrow) std::vector<TimedLaunch>();
     *out = ctx;   // returned even on failure so that ssb_last_error works; caller destroys
     SSB_CUDA(ctx, cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -377,11 +401,38 @@ extern "C" void ssb_destroy(ssb_ctx* ctx) {
     for (int l = 0; l < 16; ++l)
         if (ctx->tw[l]) cudaFree(ctx->tw[l]);
     if (ctx->window) cudaFree(ctx->window);
+    if (ctx->timed) {
+        for (auto& tl : *ctx->timed) { cudaEventDestroy(tl.a); cudaEventDestroy(tl.b); }
+        delete ctx->timed;
+    }
     delete ctx;
 }
 
 extern "C" const char* ssb_last_error(const ssb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" int64_t ssb_launch_count(const ssb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ssb_set_kernel_timing(ssb_ctx* ctx, int enable) {
+    if (!ctx) return SSB_E_INVALID_ARG;
+    ctx->timing = enable ? 1 : 0;
+    return SSB_OK;
+}
+
+extern "C" int ssb_get_kernel_timing(ssb_ctx* ctx, double* ms_sum, int64_t* counts) {
+    if (!ctx || !ms_sum || !counts || !ctx->timed) return SSB_E_INVALID_ARG;
+    for (int k = 0; k < K_COUNT; ++k) { ms_sum[k] = 0.0; counts[k] = 0; }
+    for (auto& tl : *ctx->timed) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(tl.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, tl.a, tl.b);
+        cudaEventDestroy(tl.a);
+        cudaEventDestroy(tl.b);
+        if (e != cudaSuccess) { ctx->timed->clear(); SSB_CUDA(ctx, e); }
+        ms_sum[tl.kernel] += ms;
+        counts[tl.kernel] += 1;
+    }
+    ctx->timed->clear();
+    return SSB_OK;
+}
 
 extern "C" int ssb_spec_cols(int sr) {
     const int frames = 1 + sr / SSB_HOP;
@@ -418,8 +469,10 @@ template <int LOG2N>
 static cudaError_t launch_src(ssb_ctx* ctx, const float* d_src, int S, int64_t m0, int wrap, int nw, int wofs,
                               float2* d_x, cudaStream_t st) {
     using P = FftPlan<LOG2N>;
-    fwd_src_kernel<LOG2N><<<nw, P::T, P::SMEM_ELEMS * sizeof(float2), st>>>(d_src, S, (long long)m0, wrap, wofs, d_x, ctx->tw[LOG2N]);
-    ctx->launches += 1;
+    {
+        LaunchTimer lt(ctx, K_FWD_SRC, st);
+        fwd_src_kernel<LOG2N><<<nw, P::T, P::SMEM_ELEMS * sizeof(float2), st>>>(d_src, S, (long long)m0, wrap, wofs, d_x, ctx->tw[LOG2N]);
+    }
     return cudaGetLastError();
 }
 
@@ -446,15 +499,20 @@ static cudaError_t launch_conv(ssb_ctx* ctx, const ssb_plan* plan, int B, const 
     using P = FftPlan<LOG2N>;
     const size_t smem = P::SMEM_ELEMS * sizeof(float2);
     dim3 g1(plan->max_parts * plan->n_terms, B);
-    fwd_rir_kernel<LOG2N><<<g1, P::T, smem, st>>>(d_reqs, (const float2*)d_rir_bank, (float2*)d_h, plan->max_parts,
-                                                  (long long)plan->h_elems_per_env, ctx->tw[LOG2N]);
+    {
+        LaunchTimer lt(ctx, K_FWD_RIR, st);
+        fwd_rir_kernel<LOG2N><<<g1, P::T, smem, st>>>(d_reqs, (const float2*)d_rir_bank, (float2*)d_h, plan->max_parts,
+                                                      (long long)plan->h_elems_per_env, ctx->tw[LOG2N]);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 g2(plan->n_blocks, B);
-    mac_ifft_kernel<LOG2N><<<g2, P::T, smem, st>>>(d_reqs, (const float2*)d_xpool, (const float2*)d_h, plan->max_parts,
-                                                   plan->n_terms, (long long)plan->h_elems_per_env, d_wave,
-                                                   (long long)wave_stride, plan->sr, ctx->tw[LOG2N]);
-    ctx->launches += 2;
+    {
+        LaunchTimer lt(ctx, K_MAC_IFFT, st);
+        mac_ifft_kernel<LOG2N><<<g2, P::T, smem, st>>>(d_reqs, (const float2*)d_xpool, (const float2*)d_h, plan->max_parts,
+                                                       plan->n_terms, (long long)plan->h_elems_per_env, d_wave,
+                                                       (long long)wave_stride, plan->sr, ctx->tw[LOG2N]);
+    }
     return cudaGetLastError();
 }
 
@@ -504,9 +562,11 @@ extern "C" int ssb_spectrogram_batch(ssb_ctx* ctx, int B, const float* d_wave, i
     const int frames = 1 + sr / SSB_HOP;
     const int cols = ssb_spec_cols(sr);
     dim3 g((cols + SPEC_COLS_PER_CTA - 1) / SPEC_COLS_PER_CTA, B);
-    spectrogram_kernel<<<g, SPEC_WARPS * 32, 0, (cudaStream_t)stream>>>(d_wave, (long long)wave_stride, sr, frames, cols,
-                                                                       pad_mode, d_spec, ctx->tw[9], ctx->window);
-    ctx->launches += 1;
+    {
+        LaunchTimer lt(ctx, K_SPECTROGRAM, (cudaStream_t)stream);
+        spectrogram_kernel<<<g, SPEC_WARPS * 32, 0, (cudaStream_t)stream>>>(d_wave, (long long)wave_stride, sr, frames, cols,
+                                                                           pad_mode, d_spec, ctx->tw[9], ctx->window);
+    }
     SSB_CUDA(ctx, cudaGetLastError());
     return SSB_OK;
 }

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .planning import effective_taps, window_layout
 from ._lib import PAD_MODES, REQ_DTYPE, SSB_FLAG_SILENT
 
 N_FFT, HOP, WIN, POOL, SPEC_ROWS = 512, 160, 400, 4, 65
@@ -122,6 +123,17 @@ class BatchedAudioRenderer:
             self._bank_used = need
         return ids
 
+    def bank_mark(self):
+        """Stack mark for transient RIRs (the continuous simulator renders a new RIR every step)."""
+        return (self._bank_used, len(self._rir_off))
+
+    def bank_release(self, mark):
+        """Drop every RIR added since ``mark``.  Safe while kernels are in flight: later uploads
+        are ordered after them on the same stream."""
+        self._bank_used, n = mark
+        del self._rir_off[n:]
+        del self._rir_len[n:]
+
     def set_dense_rir_bank(self, rirs: torch.Tensor) -> list:
         """Adopt an already device-resident (n, L, 2) float32 tensor as the bank (no copy)."""
         if not (rirs.is_cuda and rirs.dtype == torch.float32 and rirs.is_contiguous() and rirs.ndim == 3
@@ -166,14 +178,11 @@ class BatchedAudioRenderer:
 
     def _windows(self, source: int, offset: int, wrap: bool, out_samples: int):
         """Cached overlap-save window spectra of (clip, offset).  Returns (x_offset, nw, wofs)."""
-        P = self.P
-        nblk = -(-out_samples // P)
-        wofs = min(self.plan.max_parts - 1, -(-offset // P))
+        nblk, wofs, nw = window_layout(self.P, self.plan.max_parts, offset, out_samples)
         key = (source, offset, bool(wrap), nblk, wofs)
         hit = self._xcache.get(key)
         if hit is not None:
             return hit
-        nw = nblk + wofs
         need = nw * self.N
         if self._xpool_used + need > self._xpool.numel() // 2:
             if need > self._xpool.numel() // 2:
@@ -195,9 +204,9 @@ class BatchedAudioRenderer:
         if rir_id is None or rir_id < 0 or self._rir_len[rir_id] == 0:
             term["rir_taps"] = 0
             return
-        taps = min(self._rir_len[rir_id], offset + out_samples, self.plan.max_parts * self.P)
-        if self._rir_len[rir_id] > self.max_taps and offset + out_samples > self.max_taps:
-            raise ValueError(f"RIR {rir_id} has {self._rir_len[rir_id]} taps > max_taps={self.max_taps}")
+        taps = effective_taps(self._rir_len[rir_id], offset, out_samples)
+        if taps > self.plan.max_parts * self.P:
+            raise ValueError(f"RIR {rir_id} needs {taps} taps > max_taps={self.max_taps} the renderer was sized for")
         x_off, nw, wofs = self._windows(source, offset, wrap, out_samples)
         term["rir_offset"] = self._rir_off[rir_id]
         term["x_offset"] = x_off

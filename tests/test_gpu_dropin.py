@@ -1,0 +1,203 @@
+"""GPU tests of the drop-in boundary: the simulator mixins and Habitat sensor plugins driven like
+the reference's own classes (bare simulator objects with the attributes of SURVEY.md App. D, RIR
+wav trees on disk), compared with the oracle / the reference's golden outputs."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from oracle import audio_oracle as ao  # noqa: E402
+from oracle.ref_harness import AttrDict, write_rir  # noqa: E402
+from synth import make_rir, make_source  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location(
+    "make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+mg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mg)
+
+
+def make_sim_class():
+    from soundspaces_b200.simulator import B200AudioMixin
+
+    class FakeSoundSpacesSim(B200AudioMixin):
+        """Only the non-audio attributes/properties the reference class provides
+        (simulator.py:303-335, :568-573)."""
+
+        @property
+        def binaural_rir_dir(self):
+            return os.path.join(self.config.AUDIO.BINAURAL_RIR_DIR, self.config.SCENE_DATASET, "apartment_0")
+
+        @property
+        def current_source_sound(self):
+            return self._source_sound_dict[self._current_sound]
+
+        @property
+        def azimuth_angle(self):
+            return -(self._rotation_angle + 0) % 360
+
+        @property
+        def is_silent(self):
+            return self._episode_step_count > self._duration
+
+    return FakeSoundSpacesSim
+
+
+def make_sim(rir_root, sr, sounds, *, rotation=0, step_count=0, audio_index=0, distractor=None,
+             distractor_sound=None, receiver=0, source=1):
+    sim = make_sim_class()()
+    sim.config = AttrDict(USE_RENDERED_OBSERVATIONS=True, SCENE_DATASET="replica",
+                          AUDIO=AttrDict(RIR_SAMPLING_RATE=sr, HAS_DISTRACTOR_SOUND=distractor is not None,
+                                         BINAURAL_RIR_DIR=rir_root, EVERLASTING=True))
+    sim._episode_step_count, sim._duration = step_count, 500
+    sim._rotation_angle = rotation
+    sim._receiver_position_index, sim._source_position_index = receiver, source
+    sim._current_sound = "telephone.wav"
+    sim._source_sound_dict = dict(sounds)
+    sim._audio_index = audio_index
+    sim._audio_length = sounds["telephone.wav"].shape[0] // sr
+    sim._audiogoal_cache, sim._spectrogram_cache = {}, {}
+    if distractor is not None:
+        sim._distractor_position_index, sim._current_distractor_sound = distractor, distractor_sound
+    return sim
+
+
+def check_wave(got, ref, stride=1):
+    got, ref = np.asarray(got, np.float64)[:, ::stride], np.asarray(ref, np.float64)
+    peak = np.abs(ref).max()
+    assert (np.abs(got - ref).max() <= 1e-4 * peak) if peak else (not got.any())
+
+
+@pytest.mark.parametrize("name", sorted(mg.DISCRETE_CASES))
+def test_discrete_simulator_dropin(golden, name, tmp_path):
+    from soundspaces_b200.sensors import AudioGoalSensor, SpectrogramSensor
+    c = mg.DISCRETE_CASES[name]
+    src, rir, dsrc, drir = mg.discrete_inputs(c)
+    sr, rot = c["sr"], c.get("rotation_angle", 0)
+    az = -rot % 360
+    d = str(tmp_path)
+    if c.get("rir_mode") == "unreadable":
+        write_rir(d, "replica", "apartment_0", az, 0, 1, sr, None)
+    elif c.get("rir_mode") == "empty":
+        write_rir(d, "replica", "apartment_0", az, 0, 1, sr, np.zeros((0, 2), np.float32))
+    else:
+        write_rir(d, "replica", "apartment_0", az, 0, 1, sr, rir)
+    sounds, kw = {"telephone.wav": src}, {}
+    if dsrc is not None:
+        sounds["distractor.wav"] = dsrc
+        write_rir(d, "replica", "apartment_0", az, 0, 2, sr, drir)
+        kw = dict(distractor=2, distractor_sound="distractor.wav")
+    sim = make_sim(d, sr, sounds, rotation=rot, step_count=c.get("step_count", 0),
+                   audio_index=c.get("audio_index", 0), **kw)
+    cfg = AttrDict()
+    wave_sensor = AudioGoalSensor(sim=sim, config=cfg)
+    spec_sensor = SpectrogramSensor(sim=sim, config=cfg)
+    assert wave_sensor.uuid == "audiogoal" and spec_sensor.uuid == "spectrogram"
+    assert wave_sensor.observation_space.shape == (2, sr)
+    assert spec_sensor.observation_space.shape == ao.spectrogram_shape(sr)
+
+    wave = wave_sensor.get_observation(observations={}, episode=None)
+    gw = golden.get(f"{name}/wave")
+    stride = 1
+    if gw is None:
+        gw, stride = golden[f"{name}/wave_stride5"], 5
+    check_wave(wave, gw, stride)
+    assert wave.shape == (2, sr) and str(wave.dtype) == str(golden[f"{name}/wave_dtype"])
+    if dsrc is None:
+        assert int(golden[f"{name}/audio_index_after"]) == sim._audio_index
+        # second call is a memo hit: same object, index not advanced again (simulator.py:683-686)
+        assert wave_sensor.get_observation(observations={}, episode=None) is wave
+        assert int(golden[f"{name}/audio_index_after"]) == sim._audio_index
+        spec = spec_sensor.get_observation(observations={}, episode=None)
+        assert np.allclose(spec, golden[f"{name}/spec_reflect"], rtol=1e-4, atol=1e-5)
+        assert spec_sensor.get_observation(observations={}, episode=None) is spec
+    # fresh simulator, spectrogram first (fused device path, cache miss)
+    sim2 = make_sim(d, sr, sounds, rotation=rot, step_count=c.get("step_count", 0),
+                    audio_index=c.get("audio_index", 0), **kw)
+    spec2 = SpectrogramSensor(sim=sim2, config=cfg).get_observation(observations={}, episode=None)
+    if dsrc is None:
+        assert np.allclose(spec2, golden[f"{name}/spec_reflect"], rtol=1e-4, atol=1e-5)
+        assert int(golden[f"{name}/audio_index_after"]) == sim2._audio_index
+    else:
+        ref = ao.compute_spectrogram(ao.compute_audiogoal(src, rir, sr, distractor=dsrc, distractor_rir=drir))
+        assert np.allclose(spec2, ref, rtol=1e-4, atol=1e-5)
+    if c.get("step_count", 0) > 500:
+        assert not np.any(spec2) and not np.any(wave)
+
+
+def test_compute_spectrogram_static_on_host_array(golden):
+    """savi imports SpectrogramSensor.compute_spectrogram and calls it on host arrays."""
+    from soundspaces_b200.sensors import SpectrogramSensor
+    w = golden["a2_16k/wave"]
+    s = SpectrogramSensor.compute_spectrogram(w)
+    assert isinstance(s, np.ndarray) and s.shape == (65, 26, 2)
+    assert np.allclose(s, golden["a2_16k/spec_reflect"], rtol=1e-4, atol=1e-5)
+    assert not SpectrogramSensor.compute_spectrogram(np.zeros((2, 16000))).any()
+
+
+def test_custom_callable_gets_host_waveform(tmp_path):
+    sr = 16000
+    src, rir = make_source(1, sr), make_rir(1, 5000)
+    write_rir(str(tmp_path), "replica", "apartment_0", 0, 0, 1, sr, rir)
+    sim = make_sim(str(tmp_path), sr, {"telephone.wav": src})
+    seen = {}
+
+    def fn(audio):
+        seen["a"] = audio
+        return audio.sum(axis=1)
+    out = sim.get_current_spectrogram_observation(fn)
+    assert isinstance(seen["a"], np.ndarray) and seen["a"].shape == (2, sr) and out.shape == (2,)
+
+
+@pytest.mark.parametrize("name", sorted(mg.CONTINUOUS_CASES))
+def test_continuous_simulator_dropin(golden, name):
+    from soundspaces_b200.sensors import SpectrogramSensor
+    from soundspaces_b200.simulator import B200ContinuousAudioMixin
+    c = mg.CONTINUOUS_CASES[name]
+    src, rir, last = mg.continuous_inputs(c)
+
+    class FakeContinuousSim(B200ContinuousAudioMixin):
+        @property
+        def current_source_sound(self):
+            return self._source_sound_dict[self._current_sound]
+
+    sim = FakeContinuousSim()
+    sim.config = AttrDict(STEP_TIME=0.25, AUDIO=AttrDict(RIR_SAMPLING_RATE=c["sr"], CROSSFADE=last is not None))
+    sim._episode_step_count, sim._duration = c.get("step_count", 0), 500
+    sim._current_sound, sim._source_sound_dict = "s", {"s": src}
+    sim._current_sample_index = c["sample_index"]
+    sim._prev_sim_obs = {"audio_sensor": np.asarray(rir).T.tolist()}
+    sim._last_rir = last
+    wave = sim.get_current_audiogoal_observation()
+    check_wave(wave, golden[f"{name}/wave"])
+    spec = sim.get_current_spectrogram_observation(SpectrogramSensor.compute_spectrogram)
+    assert np.allclose(spec, golden[f"{name}/spec_reflect"], rtol=1e-4, atol=1e-5)
+    n0 = len(sim._b200_service().renderer._rir_off)
+    sim.get_current_audiogoal_observation()
+    assert len(sim._b200_service().renderer._rir_off) == n0          # transient RIRs are released
+
+
+def test_vector_batching_and_batch_obs(tmp_path):
+    from soundspaces_b200.sensors import VectorAudioObservations, batch_obs
+    sr, n = 16000, 6
+    src = make_source(2, sr)
+    d = str(tmp_path)
+    rirs = [make_rir(10 + i, 3000 + 500 * i) for i in range(n)]
+    sims = []
+    for i in range(n):
+        write_rir(d, "replica", "apartment_0", 0, i, 1, sr, rirs[i])
+        sims.append(make_sim(d, sr, {"telephone.wav": src}, receiver=i, step_count=501 if i == 4 else 0))
+    vec = VectorAudioObservations(sr)
+    out = vec.collect(sims)
+    assert out.is_cuda and out.shape == (n, 65, 26, 2)
+    launches = vec.renderer.ctx.launch_count
+    again = vec.collect(sims)                                  # all memo hits: no kernels
+    assert vec.renderer.ctx.launch_count == launches and torch.equal(out, again)
+    for i in range(n):
+        ref = ao.compute_spectrogram(ao.compute_audiogoal(src, rirs[i], sr, silent=(i == 4)).astype(np.float32))
+        assert np.allclose(out[i].cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
+    batch = batch_obs([{"spectrogram": out[i], "x": np.float32(i)} for i in range(n)], device=out.device)
+    assert batch["spectrogram"].is_cuda and torch.equal(batch["spectrogram"], out)

@@ -120,7 +120,11 @@ def test_spectrogram_only(golden, sr, pad_mode):
     got = r.spectrogram(torch.from_numpy(w).cuda()).cpu().numpy()
     for i in range(3):
         check_spec(got[i], ao.compute_spectrogram(w[i], pad_mode=pad_mode))
-    assert not got[1, :, :, 1].any()
+    # ears are packed into one complex FFT: a silent ear next to a live one sees only rounding
+    # leakage (the exact-zero contract is for fully silent steps, simulator.py:610-612)
+    assert np.abs(got[1, :, :, 1]).max() < 1e-7
+    z = r.spectrogram(torch.zeros((2, 2, sr), dtype=torch.float32, device="cuda")).cpu().numpy()
+    assert not z.any()
 
 
 def test_singing_fixture(golden):

@@ -1,0 +1,139 @@
+"""CPU tests of the host side: the overlap-save plan arithmetic against the oracle (through a
+numpy model of the kernels' dataflow), the C-ABI library's exported symbols and struct layout,
+and the env sharding over a world_size-2 gloo group."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from kernel_model import render_model
+from oracle import audio_oracle as ao
+from synth import make_rir, make_source
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def close(a, b, tol=1e-9):
+    peak = max(np.abs(b).max(), 1e-30)
+    assert np.abs(a - b).max() <= tol * peak
+
+
+@pytest.mark.parametrize("P", [2048, 4096, 8192])
+@pytest.mark.parametrize("L", [1, 100, 4096, 4097, 16000, 20000, 47999])
+def test_plan_head_mode(P, L):
+    sr = 16000
+    src, rir = make_source(1, sr).astype(np.float64), make_rir(L, L).astype(np.float64)
+    close(render_model(src, rir, sr, P, -(-48000 // P)), ao.compute_audiogoal(src, rir, sr))
+
+
+@pytest.mark.parametrize("P", [2048, 4096])
+@pytest.mark.parametrize("index", [0, 1, 2, 3])
+@pytest.mark.parametrize("L", [7001, 20000, 40000])
+def test_plan_multisecond(P, index, L):
+    sr = 16000
+    src, rir = make_source(2, 4 * sr).astype(np.float64), make_rir(L, L).astype(np.float64)
+    got = render_model(src, rir, sr, P, -(-48000 // P), offset=index * sr)
+    close(got, ao.compute_audiogoal(src, rir, sr, audio_index=index))
+
+
+@pytest.mark.parametrize("idx", [0, 4000, 12000, 44000, 46000])
+def test_plan_continuous(idx):
+    sr, P = 16000, 4096
+    src, rir = make_source(3, 3 * sr).astype(np.float64), make_rir(9, 9000).astype(np.float64)
+    got = render_model(src, rir, sr, P, 12, offset=idx, out_samples=4000, wrap=True)
+    close(got, ao.continuous_convolve_with_rir(src, rir, sr, 0.25, idx))
+
+
+def test_empty_and_fallback():
+    sr = 16000
+    src = make_source(4, sr).astype(np.float64)
+    assert not render_model(src, None, sr, 4096, 4).any()
+    assert not ao.compute_audiogoal(src, None, sr).any()
+
+
+# ---------------------------------------------------------------------------------- C ABI
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "ssb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ssb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from soundspaces_b200 import _lib
+    path = _lib.build_library()
+    lib = ctypes.CDLL(path)
+    names = header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ssb200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names, "ctypes prototypes out of sync with the header"
+    assert _lib.load_library().ssb_version() >= 100
+    assert _lib.load_library().ssb_spec_cols(16000) == 26 and _lib.load_library().ssb_spec_cols(44100) == 69
+
+
+def test_request_struct_layout_matches_c(tmp_path):
+    from soundspaces_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ssb200.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ssb_conv_term), sizeof(ssb_req),'
+                   'offsetof(ssb_conv_term, x_offset), offsetof(ssb_conv_term, rir_taps), offsetof(ssb_conv_term, x_wofs),'
+                   'offsetof(ssb_req, out_samples), offsetof(ssb_req, flags), sizeof(ssb_plan));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    t, r = _lib.TERM_DTYPE, _lib.REQ_DTYPE
+    assert vals == [t.itemsize, r.itemsize, t.fields["x_offset"][1], t.fields["rir_taps"][1], t.fields["x_wofs"][1],
+                    r.fields["out_samples"][1], r.fields["flags"][1], ctypes.sizeof(_lib.Plan)]
+
+
+def test_product_has_no_oracle_import_and_no_cpu_fallback():
+    pkg = os.path.join(ROOT, "soundspaces_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            text = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in text.replace("no CPU fallback", ""), f"{fn} mentions the oracle"
+            assert "fftconvolve" not in text or fn == "simulator.py" or "reference" in text
+    import torch
+    if not torch.cuda.is_available():
+        from soundspaces_b200 import BatchedAudioRenderer
+        with pytest.raises(RuntimeError):
+            BatchedAudioRenderer(16000, 4096, device="cuda:0")
+        with pytest.raises(RuntimeError):
+            BatchedAudioRenderer(16000, 4096, device="cpu")
+
+
+# ---------------------------------------------------------------------------------- sharding
+def _gloo_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from soundspaces_b200.distributed import gather_observations, shard_envs
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n_envs = 7
+    mine = shard_envs(n_envs, rank, world)
+    # fake "rendered" rows: row value = env index
+    local = torch.stack([torch.full((65, 3, 2), float(i)) for i in mine]) if mine else torch.zeros((0, 65, 3, 2))
+    full = gather_observations(local, n_envs, rank, world)
+    assert full.shape == (n_envs, 65, 3, 2)
+    assert all(float(full[i, 0, 0, 0]) == float(i) for i in range(n_envs))
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+
+
+def test_shard_and_gather_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_shard_envs_partition():
+    from soundspaces_b200.planning import shard_envs
+    for world in (1, 2, 4, 8):
+        parts = [shard_envs(13, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(13))
