@@ -19,6 +19,11 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# worker processes of the CPU arm are single-threaded (one env per process, like the reference's
+# VectorEnv workers): must be set before numpy/scipy are imported in the spawned children
+for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_k, "1")
 import subprocess
 import sys
 import threading

@@ -95,25 +95,18 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
     for (int s = 0; s < 16; ++s) v[s] = u[s];
 }
 
-// v[s] *= w^s for s = 1..15 given w (depth-4 product tree)
-__device__ __forceinline__ void apply_twiddle_powers(float2 (&v)[16], float2 w1) {
-    float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
-    float2 w5 = cmul(w4, w1), w6 = cmul(w3, w3), w7 = cmul(w4, w3), w8 = cmul(w4, w4);
-    v[1] = cmul(v[1], w1);
-    v[2] = cmul(v[2], w2);
-    v[3] = cmul(v[3], w3);
-    v[4] = cmul(v[4], w4);
-    v[5] = cmul(v[5], w5);
-    v[6] = cmul(v[6], w6);
-    v[7] = cmul(v[7], w7);
-    v[8] = cmul(v[8], w8);
-    v[9] = cmul(v[9], cmul(w8, w1));
-    v[10] = cmul(v[10], cmul(w8, w2));
-    v[11] = cmul(v[11], cmul(w8, w3));
-    v[12] = cmul(v[12], cmul(w8, w4));
-    v[13] = cmul(v[13], cmul(w8, w5));
-    v[14] = cmul(v[14], cmul(w8, w6));
-    v[15] = cmul(v[15], cmul(w8, w7));
+// v[s] *= w^(j s) for s = 1..15 with correctly rounded twiddles read from a table laid out
+// [s-1][j] (j < st); tp already points at column j.  (A product tree from w^1 costs fewer loads
+// but its 3-4 ulp twiddle error leaks the loudest bin into quiet ones: measured 8x the error of
+// an exact-twiddle FFT on music, see DESIGN.md "Numerics".)
+template <bool INV, bool TW_GLOBAL>
+__device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const float2* __restrict__ tp, int st) {
+#pragma unroll
+    for (int s = 1; s < 16; ++s) {
+        float2 w = TW_GLOBAL ? __ldg(tp + (s - 1) * st) : tp[(s - 1) * st];
+        if (INV) w.y = -w.y;
+        v[s] = cmul(v[s], w);
+    }
 }
 
 template <int LOG2N>
@@ -127,6 +120,14 @@ struct FftPlan {
     // shared memory (float2 elements) for the exchange buffer, with padding
     static constexpr int SMEM_ELEMS = N + N / 16;
     __host__ __device__ static constexpr int stride(int p) { return N >> (4 * (p + 1)); }
+    // twiddle table: pass p occupies 15 * stride(p) float2 at tw_offset(p), laid out [s-1][j]
+    // with value exp(-2 pi i * j * s / (16 * stride(p)))
+    __host__ __device__ static constexpr int tw_offset(int p) {
+        int o = 0;
+        for (int q = 0; q < p; ++q) o += 15 * stride(q);
+        return o;
+    }
+    static constexpr int TW_ELEMS = tw_offset(NPASS);
 };
 
 // logical element index held by thread t, register i during pass with stride st
@@ -146,8 +147,9 @@ __device__ __forceinline__ void group_sync() {
 }
 
 // Forward transform.  In: v[q] = x[t + q*T].  Out: v[i] = spectrum slot (t, i).
-// tw: global table tw[k] = exp(-2 pi i k / N), k < N.  buf: >= SMEM_ELEMS float2, private to the group.
-template <int LOG2N>
+// tw: twiddle table (FftPlan::tw_offset layout; global memory when TW_GLOBAL, else shared).
+// buf: >= SMEM_ELEMS float2, private to the group.
+template <int LOG2N, bool TW_GLOBAL = true>
 __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __restrict__ buf,
                                             const float2* __restrict__ tw) {
     using P = FftPlan<LOG2N>;
@@ -165,11 +167,7 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __re
             for (int i = 0; i < 16; ++i) v[i] = buf[pad_idx(pass_pos(t, i, st), st)];
         }
         fft16<false>(v);
-        if (st > 1) {
-            const int j = t % st;
-            float2 w1 = __ldg(&tw[j * (P::N / (16 * st))]);
-            apply_twiddle_powers(v, w1);
-        }
+        if (st > 1) apply_twiddles<false, TW_GLOBAL>(v, tw + P::tw_offset(p) + (t % st), st);
     }
     // leftover radix-M across M adjacent lanes (DIF)
     if constexpr (P::M == 2) {
@@ -194,7 +192,7 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __re
 }
 
 // Inverse transform (unscaled).  In: v[i] = spectrum slot (t, i).  Out: v[q] = N * x[t + q*T].
-template <int LOG2N>
+template <int LOG2N, bool TW_GLOBAL = true>
 __device__ __forceinline__ void fft_inverse(float2 (&v)[16], int t, float2* __restrict__ buf,
                                             const float2* __restrict__ tw) {
     using P = FftPlan<LOG2N>;
@@ -220,11 +218,7 @@ __device__ __forceinline__ void fft_inverse(float2 (&v)[16], int t, float2* __re
 #pragma unroll
     for (int p = P::NPASS - 1; p >= 0; --p) {
         const int st = P::stride(p);
-        if (st > 1) {
-            const int j = t % st;
-            float2 w1 = cconj(__ldg(&tw[j * (P::N / (16 * st))]));
-            apply_twiddle_powers(v, w1);
-        }
+        if (st > 1) apply_twiddles<true, TW_GLOBAL>(v, tw + P::tw_offset(p) + (t % st), st);
         fft16<true>(v);
         if (p > 0) {
             const int stn = P::stride(p - 1);

@@ -225,6 +225,9 @@ spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr
                    const float* __restrict__ window) {
     __shared__ float2 xbuf[SPEC_WARPS][SPEC_BUF];
     __shared__ float fsum[SPEC_WARPS][SSB_SPEC_ROWS][2];
+    __shared__ float2 stw[FftPlan<9>::TW_ELEMS];
+    for (int i = threadIdx.x; i < FftPlan<9>::TW_ELEMS; i += SPEC_WARPS * 32) stw[i] = __ldg(tw + i);
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.y;
     const int col0 = blockIdx.x * SPEC_COLS_PER_CTA;
@@ -254,7 +257,7 @@ spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr
             }
             v[q] = z;
         }
-        fft_forward<9>(v, lane, buf, tw);
+        fft_forward<9, false>(v, lane, buf, stw);
         __syncwarp();
         // natural order: k = (lane>>1) + 16 i + 256 (lane&1)
 #pragma unroll
@@ -352,6 +355,24 @@ static int setup_smem_attrs() {
     return e == cudaSuccess ? 0 : -1;
 }
 
+// twiddle table of FftPlan<LOG2N>: pass p, [s-1][j] = exp(-2 pi i j s / (16 stride(p))), rounded from double
+template <int LOG2N>
+static cudaError_t upload_twiddles(ssb_ctx* ctx) {
+    using P = FftPlan<LOG2N>;
+    std::vector<float2> h(P::TW_ELEMS);
+    for (int p = 0; p < P::NPASS; ++p) {
+        const int st = P::stride(p);
+        for (int s = 1; s < 16; ++s)
+            for (int j = 0; j < st; ++j) {
+                const double a = -2.0 * M_PI * (double)j * (double)s / (16.0 * (double)st);
+                h[P::tw_offset(p) + (s - 1) * st + j] = make_float2((float)cos(a), (float)sin(a));
+            }
+    }
+    cudaError_t e = cudaMalloc(&ctx->tw[LOG2N], h.size() * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->tw[LOG2N], h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    return e;
+}
+
 extern "C" int ssb_version(void) { return 100; }
 
 extern "C" int ssb_create(int device, ssb_ctx** out) {
@@ -368,17 +389,12 @@ extern "C" int ssb_create(int device, ssb_ctx** out) {
     SSB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) SSB_FAIL(ctx, SSB_E_CUDA, "device %d is sm_%d%d; libssb200 is built for sm_100a only", device, prop.major, prop.minor);
     ctx->sm_count = prop.multiProcessorCount;
-    for (int l : kSupportedLog2) {
-        const int n = 1 << l;
-        float2* h = new (std::nothrow) float2[n];
-        if (!h) SSB_FAIL(ctx, SSB_E_OOM, "host alloc");
-        for (int k = 0; k < n; ++k) {
-            double a = -2.0 * M_PI * (double)k / (double)n;
-            h[k] = make_float2((float)cos(a), (float)sin(a));
-        }
-        cudaError_t e = cudaMalloc(&ctx->tw[l], n * sizeof(float2));
-        if (e == cudaSuccess) e = cudaMemcpy(ctx->tw[l], h, n * sizeof(float2), cudaMemcpyHostToDevice);
-        delete[] h;
+    {
+        cudaError_t e = cudaSuccess;
+        if (e == cudaSuccess) e = upload_twiddles<9>(ctx);
+        if (e == cudaSuccess) e = upload_twiddles<12>(ctx);
+        if (e == cudaSuccess) e = upload_twiddles<13>(ctx);
+        if (e == cudaSuccess) e = upload_twiddles<14>(ctx);
         SSB_CUDA(ctx, e);
     }
     {

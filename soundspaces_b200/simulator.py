@@ -82,12 +82,15 @@ class AudioRenderService:
         return self.renderer.add_rirs([np.asarray(rir, dtype=np.float32)])[0]
 
     def source(self, key, samples) -> int:
-        k = (key, len(samples))
-        sid = self._src_ids.get(k)
-        if sid is None:
-            sid = self.renderer.add_source(np.asarray(samples, dtype=np.float32))
-            self._src_ids[k] = sid
-        return sid
+        """Device copy of a decoded clip, memoised per array object (the reference memoises the
+        decoded clip per sound name in ``_source_sound_dict``, simulator.py:595-600; keying on the
+        array keeps two simulators with different clips under one name apart)."""
+        k = (key, len(samples), id(samples))
+        hit = self._src_ids.get(k)
+        if hit is None:
+            hit = (self.renderer.add_source(np.asarray(samples, dtype=np.float32)), samples)  # keep the array alive
+            self._src_ids[k] = hit
+        return hit[0]
 
 
 SPECTROGRAM_NATIVE_ATTR = "_b200_native_spectrogram"

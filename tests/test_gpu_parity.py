@@ -227,6 +227,9 @@ def test_error_reporting():
     r = renderer(16000, 6000)
     with pytest.raises(RuntimeError, match="log2n"):
         r.ctx.make_plan(16000, 100, 1, 11)
-    with pytest.raises(RuntimeError):
+    with pytest.raises(ValueError):
         r.spectrogram(torch.zeros((1, 2, 100), device="cuda"))
+    import ctypes
+    rc = r.lib.ssb_spectrogram_batch(r.ctx.handle, 1, None, 100, 100, 0, None, None)
+    assert rc == -1 and b"ssb_spectrogram_batch" in r.lib.ssb_last_error(r.ctx.handle)
     assert _lib.load_library().ssb_version() >= 100
