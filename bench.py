@@ -270,7 +270,7 @@ def run_gpu(args, rank, local_rank, world):
     r.ctx.set_kernel_timing(False)
 
     # ---- end to end through the host-buffer C-ABI entry ("e2e")
-    hs = r.make_host_session(B, TAPS, want_wave=False)
+    hs = r.make_host_session(B, TAPS, want_wave=False, n_chunks=args.chunks)
     hs.h_rir.numpy()[:] = bank_host[:B]
     hs.set_requests(sid, silent=sil)
     for _ in range(max(3, args.warmup // 4)):
@@ -321,7 +321,7 @@ def run_gpu(args, rank, local_rank, world):
             },
             "e2e": {"value": B * world * e2e_steps / (e2e_ms_max * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes,
-                    "ms_per_step": e2e_ms_max / e2e_steps, "api": "ssb_render_batch_host (pinned host RIRs in, host spectrograms out)",
+                    "ms_per_step": e2e_ms_max / e2e_steps, "api": f"ssb_render_batch_host (pinned host RIRs in, host spectrograms out), {args.chunks} pipelined chunks",
                     "checksum": checksum},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -345,6 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=0)
+    ap.add_argument("--chunks", type=int, default=4, help="pipeline depth of the host-buffer (e2e) entry")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames-per-core", type=int, default=150)
     args = ap.parse_args()

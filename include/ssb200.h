@@ -108,6 +108,10 @@ int64_t ssb_launch_count(const ssb_ctx* ctx);
 int ssb_set_kernel_timing(ssb_ctx* ctx, int enable);
 int ssb_get_kernel_timing(ssb_ctx* ctx, double* ms_sum /*[SSB_N_KERNELS]*/, int64_t* counts /*[SSB_N_KERNELS]*/);
 
+/* Profiling only: ablation switches (1 skip the spectrum MAC, 2 skip the inverse FFT, 4 skip the
+ * waveform loads of the spectrogram kernel, 8 skip its FFT).  Results are wrong when non-zero. */
+int ssb_set_debug(ssb_ctx* ctx, int flags);
+
 /* Fill a plan.  log2n = 0 picks the default (13). */
 int ssb_make_plan(ssb_ctx* ctx, int sr, int max_taps, int n_terms, int log2n, ssb_plan* plan);
 
@@ -140,13 +144,16 @@ int ssb_render_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d
                      const float* d_rir_bank, const void* d_xpool, void* d_hscratch,
                      float* d_wave, int64_t wave_stride, int pad_mode, float* d_spec, void* stream);
 
-/* Host-buffer entry: copies h_rir (rir_bytes) and h_reqs to the device staging buffers the
- * caller provides, renders, and copies the spectrogram (and the waveform when h_wave != NULL,
- * densely packed [B][2][sr]) back to the host.  All on `stream`; the caller synchronises. */
+/* Host-buffer entry: copies h_rir (rir_bytes; offsets in h_reqs index it) and h_reqs to the device
+ * staging buffers the caller provides, renders, and copies the spectrogram (and the waveform when
+ * h_wave != NULL, densely packed [B][2][sr]) back to the host.  n_chunks > 1 splits the batch and
+ * overlaps H2D copy / kernels / D2H copy of consecutive chunks on internal copy streams; either way
+ * all of it is ordered after prior work on `stream` and `stream` completes when the results have
+ * landed; the caller synchronises. */
 int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* h_reqs,
                           const float* h_rir, int64_t rir_bytes, float* d_rir_staging, ssb_req* d_reqs_staging,
                           const void* d_xpool, void* d_hscratch, float* d_wave, int64_t wave_stride,
-                          int pad_mode, float* d_spec, float* h_spec, float* h_wave, void* stream);
+                          int pad_mode, float* d_spec, float* h_spec, float* h_wave, int n_chunks, void* stream);
 
 /* PCM helpers.  decode: float32(x) / 32768 (exact).  encode mode 0: round(x*32768) saturated;
  * mode 1: trunc(x*32767) saturated (interactive_demo.py:110). */

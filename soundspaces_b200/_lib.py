@@ -43,6 +43,7 @@ EXPORTS = {
     "ssb_destroy": (None, [C.c_void_p]),
     "ssb_last_error": (C.c_char_p, [C.c_void_p]),
     "ssb_launch_count": (C.c_int64, [C.c_void_p]),
+    "ssb_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "ssb_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ssb_get_kernel_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ssb_make_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Plan)]),
@@ -59,7 +60,7 @@ EXPORTS = {
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "ssb_render_batch_host": (C.c_int, [C.c_void_p, C.POINTER(Plan), C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ssb_pcm16_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ssb_pcm16_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
 }

@@ -13,6 +13,20 @@
 // overlap-save convolution never needs a reordering pass.  freq_of_slot()
 // gives the permutation for callers that need natural order (the STFT).
 //
+// Twiddles: the 15 inter-pass twiddles w^(j s), s = r + 4m, are applied in two
+// factors inside the 4x4 butterfly -- w^(j r) between the two radix-4 stages and
+// w^(4 j m) after the second -- so a thread needs only SIX correctly rounded table
+// entries per pass (w^j, w^2j, w^3j, w^4j, w^8j, w^12j) instead of fifteen.  Pass 0
+// (stride T: one distinct set per thread) is read from global memory early by the
+// caller; the later passes (stride <= 64) come from a small table staged in shared
+// memory.  (A product tree from w^1 alone is cheaper still but its 3-4 ulp error
+// leaks the loudest bin into quiet ones: 8x the error on music, DESIGN.md "Numerics".)
+//
+// Exchanges: one padding rule per transform size keeps every access pattern
+// bank-conflict free and makes the region a group of stride(p-1) threads touches in
+// the exchange before pass p private to that group, so exchanges whose group is one
+// warp only need __syncwarp().
+//
 // No cuFFT, no library code: this is the hot loop of the SoundSpaces audio
 // path (scipy.signal.fftconvolve at soundspaces/simulator.py:630-647 and
 // librosa.stft at soundspaces/tasks/nav.py:92 in the reference).
@@ -26,7 +40,10 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
 // a * (-i) and a * (+i)
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
 __device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }
@@ -68,9 +85,37 @@ __device__ __forceinline__ float2 mul_w16(float2 a) {
     else return mul_cs<INV>(a, -C1, -S1);        // K == 9
 }
 
-// 16-point DFT in registers: v[s] <- sum_q v[q] * w16^(+-q s)
-template <bool INV>
-__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+// the six inter-pass twiddles of one thread for one pass: r[k-1] = w^(j k), m[k-1] = w^(4 j k), k = 1..3
+struct Tw6 {
+    float2 r[3];
+    float2 m[3];
+};
+
+// table rows [6][st]: w^j, w^2j, w^3j, w^4j, w^8j, w^12j with w = exp(-2 pi i / (16 st)); tab points at column 0
+template <bool GLOBAL>
+__device__ __forceinline__ Tw6 load_tw6(const float2* __restrict__ tab, int st, int j) {
+    Tw6 w;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        w.r[k] = GLOBAL ? __ldg(tab + k * st + j) : tab[k * st + j];
+        w.m[k] = GLOBAL ? __ldg(tab + (3 + k) * st + j) : tab[(3 + k) * st + j];
+    }
+    return w;
+}
+
+// 16-point DFT in registers with the inter-pass twiddles folded in.
+//   forward (DIF):  v[s] <- w^(j s) * sum_q v[q] w16^(q s)
+//   inverse (DIT):  v[q] <- sum_s conj(w^(j s)) v[s] conj(w16)^(q s)
+// TW = false skips the inter-pass twiddles (stride-1 pass: j == 0 for every thread).
+template <bool INV, bool TW>
+__device__ __forceinline__ void fft16(float2 (&v)[16], const Tw6& w) {
+    if constexpr (INV && TW) {
+        // input s = r + 4m sits in v[s]; undo w^(4 j m)
+#pragma unroll
+        for (int m = 1; m < 4; ++m)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r + 4 * m] = cmulc(v[r + 4 * m], w.m[m - 1]);
+    }
     // stage 1: 4-point DFTs over q = c + 4d (d = 0..3); result a[c][r] left in v[c + 4r]
 #pragma unroll
     for (int c = 0; c < 4; ++c) bfly4<INV>(v[c], v[c + 4], v[c + 8], v[c + 12]);
@@ -84,29 +129,37 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
     v[7] = mul_w16<INV, 3>(v[7]);
     v[11] = mul_w16<INV, 6>(v[11]);
     v[15] = mul_w16<INV, 9>(v[15]);
+    if constexpr (TW) {
+        if constexpr (!INV) {
+            // forward: a[c][r] (in v[c + 4r]) *= w^(j r)
+#pragma unroll
+            for (int r = 1; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c + 4 * r] = cmul(v[c + 4 * r], w.r[r - 1]);
+        } else {
+            // inverse: element (c' = the forward's r, r') in v[c' + 4r'] *= conj(w^(j c'))
+#pragma unroll
+            for (int c = 1; c < 4; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) v[c + 4 * r] = cmulc(v[c + 4 * r], w.r[c - 1]);
+        }
+    }
     // stage 2: 4-point DFTs over c for each r; output s = r + 4m is left in v[4r + m]
 #pragma unroll
     for (int r = 0; r < 4; ++r) bfly4<INV>(v[4 * r], v[4 * r + 1], v[4 * r + 2], v[4 * r + 3]);
+    if constexpr (TW && !INV) {
+        // forward: X[r + 4m] (in v[4r + m]) *= w^(4 j m)
+#pragma unroll
+        for (int m = 1; m < 4; ++m)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[4 * r + m] = cmul(v[4 * r + m], w.m[m - 1]);
+    }
     // un-transpose: out[s] = v[4*(s%4) + s/4]
     float2 u[16];
 #pragma unroll
     for (int s = 0; s < 16; ++s) u[s] = v[4 * (s & 3) + (s >> 2)];
 #pragma unroll
     for (int s = 0; s < 16; ++s) v[s] = u[s];
-}
-
-// v[s] *= w^(j s) for s = 1..15 with correctly rounded twiddles read from a table laid out
-// [s-1][j] (j < st); tp already points at column j.  (A product tree from w^1 costs fewer loads
-// but its 3-4 ulp twiddle error leaks the loudest bin into quiet ones: measured 8x the error of
-// an exact-twiddle FFT on music, see DESIGN.md "Numerics".)
-template <bool INV, bool TW_GLOBAL>
-__device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const float2* __restrict__ tp, int st) {
-#pragma unroll
-    for (int s = 1; s < 16; ++s) {
-        float2 w = TW_GLOBAL ? __ldg(tp + (s - 1) * st) : tp[(s - 1) * st];
-        if (INV) w.y = -w.y;
-        v[s] = cmul(v[s], w);
-    }
 }
 
 template <int LOG2N>
@@ -117,57 +170,68 @@ struct FftPlan {
     static constexpr int M = N >> (4 * NPASS);             // leftover radix (lanes)
     static_assert(M == 1 || M == 2 || M == 4, "supported sizes: 2^{8,9,10,12,13,14}");
     static_assert(T >= 32 || T == 16, "group must be whole warps");
+    __host__ __device__ static constexpr int stride(int p) { return N >> (4 * (p + 1)); }
+    // exchange-buffer padding: PADST float2 after every 16*PADST elements, PADST = stride of the
+    // last pass (none needed when that is >= 16)
+    static constexpr int PADST = stride(NPASS - 1) >= 16 ? 0 : stride(NPASS - 1);
     // shared memory (float2 elements) for the exchange buffer, with padding
     static constexpr int SMEM_ELEMS = N + N / 16;
-    __host__ __device__ static constexpr int stride(int p) { return N >> (4 * (p + 1)); }
-    // twiddle table: pass p occupies 15 * stride(p) float2 at tw_offset(p), laid out [s-1][j]
-    // with value exp(-2 pi i * j * s / (16 * stride(p)))
+    // twiddle table: pass p occupies 6 * stride(p) float2 at tw_offset(p), rows
+    // exp(-2 pi i * j * e / (16 * stride(p))) for e in {1, 2, 3, 4, 8, 12}, j < stride(p)
     __host__ __device__ static constexpr int tw_offset(int p) {
         int o = 0;
-        for (int q = 0; q < p; ++q) o += 15 * stride(q);
+        for (int q = 0; q < p; ++q) o += 6 * stride(q);
         return o;
     }
     static constexpr int TW_ELEMS = tw_offset(NPASS);
+    // passes >= 1 ("small" table, staged in shared memory by the kernels)
+    static constexpr int TW_SMALL_OFFSET = tw_offset(1);
+    static constexpr int TW_SMALL_ELEMS = TW_ELEMS - TW_SMALL_OFFSET;
 };
 
 // logical element index held by thread t, register i during pass with stride st
 __device__ __forceinline__ int pass_pos(int t, int i, int st) {
     return (t / st) * (16 * st) + (t % st) + i * st;
 }
-// padding that makes the exchange next to a pass of (fine) stride st bank-conflict free:
-// st float2 of padding after every 16*st elements (none needed when st >= 16)
-__device__ __forceinline__ int pad_idx(int l, int st) {
-    return st >= 16 ? l : l + st * (l / (16 * st));
+template <int PADST>
+__device__ __forceinline__ int pad_idx(int l) {
+    if constexpr (PADST == 0) return l;
+    else return l + PADST * (l / (16 * PADST));
 }
 
-template <int T>
-__device__ __forceinline__ void group_sync() {
-    if constexpr (T <= 32) __syncwarp();
-    else __syncthreads();                                  // group == CTA
+// barrier among the G consecutive threads that share an exchange region
+template <int G>
+__device__ __forceinline__ void group_barrier() {
+    if constexpr (G <= 32) __syncwarp();
+    else __syncthreads();                                  // G > 32 only occurs with group == CTA (or 2 warps of it)
 }
 
 // Forward transform.  In: v[q] = x[t + q*T].  Out: v[i] = spectrum slot (t, i).
-// tw: twiddle table (FftPlan::tw_offset layout; global memory when TW_GLOBAL, else shared).
-// buf: >= SMEM_ELEMS float2, private to the group.
-template <int LOG2N, bool TW_GLOBAL = true>
-__device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __restrict__ buf,
-                                            const float2* __restrict__ tw) {
+// w0: pass-0 twiddles of this thread (load_tw6 at column t of the pass-0 table), loaded by the
+//     caller so the loads can be issued early.
+// stw: table of passes >= 1 (pass p at FftPlan::tw_offset(p) - TW_SMALL_OFFSET), normally in shared memory.
+// buf: >= SMEM_ELEMS float2, private to the group; the caller orders other uses of buf.
+template <int LOG2N>
+__device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __restrict__ buf, const Tw6& w0,
+                                            const float2* __restrict__ stw) {
     using P = FftPlan<LOG2N>;
+    fft16<false, true>(v, w0);
 #pragma unroll
-    for (int p = 0; p < P::NPASS; ++p) {
-        const int st = P::stride(p);
-        if (p > 0) {
-            // exchange: written with pass p-1 layout, read with pass p layout
-            const int stp = P::stride(p - 1);
-            if (p > 1) group_sync<P::T>();
+    for (int p = 1; p < P::NPASS; ++p) {
+        const int st = P::stride(p), stp = P::stride(p - 1);
+        // exchange: written with pass p-1 layout, read with pass p layout; shared by stp threads
+        if (p > 1) { if (stp <= 32) __syncwarp(); else __syncthreads(); }      // previous readers of this region
 #pragma unroll
-            for (int i = 0; i < 16; ++i) buf[pad_idx(pass_pos(t, i, stp), st)] = v[i];
-            group_sync<P::T>();
+        for (int i = 0; i < 16; ++i) buf[pad_idx<P::PADST>(pass_pos(t, i, stp))] = v[i];
+        if (stp <= 32) __syncwarp(); else __syncthreads();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = buf[pad_idx(pass_pos(t, i, st), st)];
+        for (int i = 0; i < 16; ++i) v[i] = buf[pad_idx<P::PADST>(pass_pos(t, i, st))];
+        if (st > 1) {
+            const Tw6 w = load_tw6<false>(stw + (P::tw_offset(p) - P::TW_SMALL_OFFSET), st, t % st);
+            fft16<false, true>(v, w);
+        } else {
+            fft16<false, false>(v, w0);
         }
-        fft16<false>(v);
-        if (st > 1) apply_twiddles<false, TW_GLOBAL>(v, tw + P::tw_offset(p) + (t % st), st);
     }
     // leftover radix-M across M adjacent lanes (DIF)
     if constexpr (P::M == 2) {
@@ -192,9 +256,11 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __re
 }
 
 // Inverse transform (unscaled).  In: v[i] = spectrum slot (t, i).  Out: v[q] = N * x[t + q*T].
-template <int LOG2N, bool TW_GLOBAL = true>
+// gtw0: pass-0 table (column 0; global memory when TW0_GLOBAL); its six entries are fetched before
+// the last exchange so the latency overlaps it.  stw: as for fft_forward.
+template <int LOG2N, bool TW0_GLOBAL = true>
 __device__ __forceinline__ void fft_inverse(float2 (&v)[16], int t, float2* __restrict__ buf,
-                                            const float2* __restrict__ tw) {
+                                            const float2* __restrict__ gtw0, const float2* __restrict__ stw) {
     using P = FftPlan<LOG2N>;
     if constexpr (P::M == 2) {
         const bool up = t & 1;
@@ -215,21 +281,28 @@ __device__ __forceinline__ void fft_inverse(float2 (&v)[16], int t, float2* __re
             v[i] = up2 ? csub(o, r) : cadd(r, o);
         }
     }
+    Tw6 w0;
+    if constexpr (P::NPASS == 1) w0 = load_tw6<TW0_GLOBAL>(gtw0, P::stride(0), t);
 #pragma unroll
-    for (int p = P::NPASS - 1; p >= 0; --p) {
-        const int st = P::stride(p);
-        if (st > 1) apply_twiddles<true, TW_GLOBAL>(v, tw + P::tw_offset(p) + (t % st), st);
-        fft16<true>(v);
-        if (p > 0) {
-            const int stn = P::stride(p - 1);
-            if (p < P::NPASS - 1) group_sync<P::T>();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) buf[pad_idx(pass_pos(t, i, st), st)] = v[i];
-            group_sync<P::T>();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = buf[pad_idx(pass_pos(t, i, stn), st)];
+    for (int p = P::NPASS - 1; p >= 1; --p) {
+        const int st = P::stride(p), stn = P::stride(p - 1);
+        if (st > 1) {
+            const Tw6 w = load_tw6<false>(stw + (P::tw_offset(p) - P::TW_SMALL_OFFSET), st, t % st);
+            fft16<true, true>(v, w);
+        } else {
+            fft16<true, false>(v, w0);
         }
+        if (p == 1) w0 = load_tw6<TW0_GLOBAL>(gtw0, P::stride(0), t);      // in flight during the exchange
+        // exchange: written with pass p layout, read with pass p-1 layout; shared by stn threads.
+        // The region was last read (previous exchange) by this thread's st-group only.
+        if (p < P::NPASS - 1) { if (st <= 32) __syncwarp(); else __syncthreads(); }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) buf[pad_idx<P::PADST>(pass_pos(t, i, st))] = v[i];
+        if (stn <= 32) __syncwarp(); else __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = buf[pad_idx<P::PADST>(pass_pos(t, i, stn))];
     }
+    fft16<true, true>(v, w0);
 }
 
 // frequency index of spectrum slot (thread t, register i)

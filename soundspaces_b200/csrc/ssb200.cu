@@ -24,6 +24,7 @@ using namespace ssb;
 // context
 // ---------------------------------------------------------------------------
 enum { K_FWD_RIR = 0, K_MAC_IFFT = 1, K_SPECTROGRAM = 2, K_FWD_SRC = 3, K_COUNT = SSB_N_KERNELS };
+#define SSB_MAX_CHUNKS 32
 struct TimedLaunch { int kernel; cudaEvent_t a, b; };
 
 struct ssb_ctx {
@@ -34,6 +35,9 @@ struct ssb_ctx {
     int64_t launches;
     // optional per-kernel CUDA-event timing (bench.py roofline); see ssb_set_kernel_timing
     int timing;
+    cudaStream_t s_h2d, s_d2h;                     // copy streams of the pipelined host entry
+    cudaEvent_t ev[2 * SSB_MAX_CHUNKS + 2];
+    int debug;           // ablation switches for profiling (ssb_set_debug); 0 in production
     std::vector<TimedLaunch>* timed;
     char err[512];
 };
@@ -80,6 +84,13 @@ __device__ __forceinline__ void store_slots(float2* __restrict__ dst, const floa
     for (int i = 0; i < 16; ++i) dst[i * T + t] = v[i];
 }
 
+// copy the twiddle rows of passes >= 1 into shared memory (a few hundred float2)
+template <int LOG2N>
+__device__ __forceinline__ void stage_small_twiddles(float2* __restrict__ stw, const float2* __restrict__ tw, int t) {
+    using P = FftPlan<LOG2N>;
+    for (int i = t; i < P::TW_SMALL_ELEMS; i += P::T) stw[i] = __ldg(tw + P::TW_SMALL_OFFSET + i);
+}
+
 // grid (max_parts * n_terms, B); block T.  H[env][term][p][N] in slot order.
 template <int LOG2N>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::T)
@@ -88,6 +99,7 @@ fwd_rir_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ rir_
                const float2* __restrict__ tw) {
     using P = FftPlan<LOG2N>;
     extern __shared__ float2 smem[];
+    float2* stw = smem + P::SMEM_ELEMS;
     constexpr int PART = P::N / 2;
     const int env = blockIdx.y;
     const int term = blockIdx.x / max_parts;
@@ -106,7 +118,9 @@ fwd_rir_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ rir_
     }
 #pragma unroll
     for (int q = 8; q < 16; ++q) v[q] = make_float2(0.f, 0.f);
-    fft_forward<LOG2N>(v, t, smem, tw);
+    const Tw6 w0 = load_tw6<true>(tw, P::T, t);
+    stage_small_twiddles<LOG2N>(stw, tw, t);           // visible after the first exchange barrier
+    fft_forward<LOG2N>(v, t, smem, w0, stw);
     float2* dst = H + (long long)env * h_elems_per_env + ((long long)term * max_parts + p) * P::N;
     store_slots<LOG2N>(dst, v, t);
 }
@@ -119,9 +133,12 @@ fwd_src_kernel(const float* __restrict__ src, int S, long long m0, int wrap, int
                float2* __restrict__ X, const float2* __restrict__ tw) {
     using P = FftPlan<LOG2N>;
     extern __shared__ float2 smem[];
+    float2* stw = smem + P::SMEM_ELEMS;
     constexpr int PART = P::N / 2;
     const int j = blockIdx.x;
     const int t = threadIdx.x;
+    const Tw6 w0 = load_tw6<true>(tw, P::T, t);
+    stage_small_twiddles<LOG2N>(stw, tw, t);
     const long long base = m0 + (long long)(j - wofs - 1) * PART;
     float2 v[16];
 #pragma unroll
@@ -134,25 +151,28 @@ fwd_src_kernel(const float* __restrict__ src, int S, long long m0, int wrap, int
         }
         v[q] = make_float2(x, 0.f);
     }
-    fft_forward<LOG2N>(v, t, smem, tw);
+    fft_forward<LOG2N>(v, t, smem, w0, stw);
     store_slots<LOG2N>(X + (long long)j * P::N, v, t);
 }
 
 // ---------------------------------------------------------------------------
 // multiply-accumulate over partitions + inverse FFT + emit
-// grid (n_blocks, B); block T.
+// grid (B, n_blocks); block T.
 // ---------------------------------------------------------------------------
 template <int LOG2N>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::T)
 mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpool,
                 const float2* __restrict__ H, int max_parts, int n_terms, long long h_elems_per_env,
                 float* __restrict__ wave, long long wave_stride, int sr,
-                const float2* __restrict__ tw) {
+                const float2* __restrict__ tw, int dbg) {
     using P = FftPlan<LOG2N>;
     extern __shared__ float2 smem[];
+    float2* stw = smem + P::SMEM_ELEMS;
     constexpr int PART = P::N / 2;
-    const int b = blockIdx.x;
-    const int env = blockIdx.y;
+    // env is the fastest block index: CTAs resident together work on the same block b of different
+    // envs and read the same source windows X[b-p] (one L2->L1 fill serves both)
+    const int env = blockIdx.x;
+    const int b = blockIdx.y;
     const int t = threadIdx.x;
     const ssb_req& rq = reqs[env];
     float* __restrict__ wl = wave + (long long)env * 2 * wave_stride;
@@ -176,7 +196,7 @@ mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
     for (int i = 0; i < 16; ++i) acc[i] = make_float2(0.f, 0.f);
     for (int term = 0; term < n_terms; ++term) {
         const ssb_conv_term& ct = rq.term[term];
-        if (ct.rir_taps <= 0) continue;
+        if (ct.rir_taps <= 0 || (dbg & 1)) continue;
         const int nparts = min((ct.rir_taps + PART - 1) / PART, max_parts);
         const float2* __restrict__ Hb = H + (long long)env * h_elems_per_env + (long long)term * max_parts * P::N;
         const float2* __restrict__ Xb = xpool + ct.x_offset;
@@ -196,7 +216,9 @@ mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
             }
         }
     }
-    fft_inverse<LOG2N>(acc, t, smem, tw);
+    stage_small_twiddles<LOG2N>(stw, tw, t);
+    __syncthreads();
+    if (!(dbg & 2)) fft_inverse<LOG2N>(acc, t, smem, tw, stw);
     constexpr float scale = 1.0f / (float)P::N;
 #pragma unroll
     for (int q = 8; q < 16; ++q) {
@@ -210,54 +232,72 @@ mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
 }
 
 // ---------------------------------------------------------------------------
-// spectrogram: one warp per STFT frame, 8 frames (2 pooled columns) per CTA
-// grid (ceil(cols/2), B); block 256
+// spectrogram: one warp per POOLED COLUMN (4 consecutive STFT frames), warps fully independent
+// (only __syncwarp): frame + pad + Hann + packed FFT-512 + |.| per ear, magnitudes accumulated
+// over the 4 frames in registers, pooled over 4 bins with two shuffles, log1p, store.
 // ---------------------------------------------------------------------------
-constexpr int SPEC_WARPS = 8;
-constexpr int SPEC_COLS_PER_CTA = SPEC_WARPS / SSB_POOL;
 constexpr int SPEC_BUF = 512 + 32;
+
+// sqrt.approx.f32: one MUFU, max relative error 2^-23 (the IEEE sqrtf expands to ~8 instructions)
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ int nat_idx(int k) { return k + ((k >> 8) << 3); }   // de-conflict k and 256+k
 
-__global__ void __launch_bounds__(SPEC_WARPS * 32)
-spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr, int n_frames, int cols,
-                   int pad_mode, float* __restrict__ out, const float2* __restrict__ tw,
-                   const float* __restrict__ window) {
-    __shared__ float2 xbuf[SPEC_WARPS][SPEC_BUF];
-    __shared__ float fsum[SPEC_WARPS][SSB_SPEC_ROWS][2];
-    __shared__ float2 stw[FftPlan<9>::TW_ELEMS];
-    for (int i = threadIdx.x; i < FftPlan<9>::TW_ELEMS; i += SPEC_WARPS * 32) stw[i] = __ldg(tw + i);
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.y;
-    const int col0 = blockIdx.x * SPEC_COLS_PER_CTA;
-    const int f = col0 * SSB_POOL + warp;
-    const float* __restrict__ yl = wave + (long long)env * 2 * wave_stride;
-    const float* __restrict__ yr = yl + wave_stride;
-    float2* buf = xbuf[warp];
-    if (f < n_frames) {
-        float2 v[16];
+// Samples: element idx = lane + 32 q of frame f is sample 160 f + idx - 256, and 160 = 5 * 32, so
+// over the 4 frames of a column lane `lane` only ever touches x_j = y[n0 + lane + 32 j], j = 1..29
+// (frame fr uses j = q + 5 fr): each frame needs just 5 new samples per ear; they are fetched
+// before the previous frame's FFT and shifted into a 14-deep register window.
+template <bool REFLECT, bool INTERIOR>
+__device__ __forceinline__ float spec_sample(const float* __restrict__ y, int n, int sr) {
+    if (INTERIOR) return __ldg(y + n);
+    if (REFLECT) {                       // np.pad(y, 256, mode='reflect'): librosa < 0.10
+        if (n < 0) n = -n;
+        if (n >= sr) n = 2 * (sr - 1) - n;
+        n = max(0, min(n, sr - 1));      // only reached by frames past the end (weight 0)
+        return __ldg(y + n);
+    }
+    return (n >= 0 && n < sr) ? __ldg(y + n) : 0.f;   // mode='constant': librosa >= 0.10
+}
+
+// One pooled column (4 frames) by one warp.  INTERIOR: every sample in range and all 4 frames real.
+template <bool REFLECT, bool INTERIOR>
+__device__ __forceinline__ void spec_column(const float* __restrict__ yl, const float* __restrict__ yr, int sr,
+                                            int n_frames, int col, int lane, float2* __restrict__ buf,
+                                            const float2* __restrict__ stw, const float* __restrict__ swin,
+                                            float (&accl)[8], float (&accr)[8], float& acc64l, float& acc64r, int dbg) {
+    const Tw6 w0 = load_tw6<true>(stw, 32, lane);
+    const int n0 = col * SSB_POOL * SSB_HOP - SSB_N_FFT / 2 + lane;          // sample of x_0 for this lane
+    float xl[15], xr[15];                                                    // window of the current frame: x[q], q = 1..14
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int idx = lane + 32 * q;
-            float2 z = make_float2(0.f, 0.f);
-            if (idx >= (SSB_N_FFT - SSB_WIN) / 2 && idx < (SSB_N_FFT + SSB_WIN) / 2) {
-                int n = f * SSB_HOP + idx - SSB_N_FFT / 2;
-                bool ok = true;
-                if (pad_mode == SSB_PAD_REFLECT) {
-                    if (n < 0) n = -n;
-                    if (n >= sr) n = 2 * (sr - 1) - n;
-                } else {
-                    ok = n >= 0 && n < sr;
-                }
-                if (ok) {
-                    float w = __ldg(window + idx);
-                    z = make_float2(w * __ldg(yl + n), w * __ldg(yr + n));
-                }
-            }
-            v[q] = z;
+    for (int q = 1; q < 15; ++q) {
+        xl[q] = (dbg & 4) ? 0.f : spec_sample<REFLECT, INTERIOR>(yl, n0 + 32 * q, sr);
+        xr[q] = (dbg & 4) ? 0.f : spec_sample<REFLECT, INTERIOR>(yr, n0 + 32 * q, sr);
+    }
+#pragma unroll 1
+    for (int fr = 0; fr < SSB_POOL; ++fr) {
+        // prefetch the 5 new samples of the next frame (j = 15 + 5 fr ..); latency hides behind this frame's FFT
+        float nl[5], nr[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int n = n0 + 32 * (15 + 5 * fr + u);
+            const bool need = fr + 1 < SSB_POOL && !(dbg & 4);
+            nl[u] = need ? spec_sample<REFLECT, INTERIOR>(yl, n, sr) : 0.f;
+            nr[u] = need ? spec_sample<REFLECT, INTERIOR>(yr, n, sr) : 0.f;
         }
-        fft_forward<9, false>(v, lane, buf, stw);
+        const bool f_ok = INTERIOR || (col * SSB_POOL + fr < n_frames);     // frames past the end add 0 (block_reduce pads with 0)
+        float2 v[16];
+        v[0] = make_float2(0.f, 0.f);                          // idx < 56 and idx >= 456 lie outside the 400-tap window
+        v[15] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 1; q < 15; ++q) {
+            const float w = f_ok ? __ldg(swin + lane + 32 * q) : 0.f;  // centre-padded Hann: 0 for idx < 56, idx >= 456
+            v[q] = make_float2(w * xl[q], w * xr[q]);
+        }
+        if (!(dbg & 8)) fft_forward<9>(v, lane, buf, w0, stw + FftPlan<9>::TW_SMALL_OFFSET);
         __syncwarp();
         // natural order: k = (lane>>1) + 16 i + 256 (lane&1)
 #pragma unroll
@@ -267,40 +307,70 @@ spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int k = lane + 32 * m;
-            float2 a = buf[nat_idx(k)];
-            float2 bb = buf[nat_idx((SSB_N_FFT - k) & (SSB_N_FFT - 1))];
-            float lx = a.x + bb.x, ly = a.y - bb.y;      // A + conj(B)
-            float rx = a.x - bb.x, ry = a.y + bb.y;      // A - conj(B)
-            float ml = 0.5f * sqrtf(lx * lx + ly * ly);
-            float mr = 0.5f * sqrtf(rx * rx + ry * ry);
-            ml += __shfl_xor_sync(0xffffffffu, ml, 1);
-            mr += __shfl_xor_sync(0xffffffffu, mr, 1);
-            ml += __shfl_xor_sync(0xffffffffu, ml, 2);
-            mr += __shfl_xor_sync(0xffffffffu, mr, 2);
-            if ((lane & 3) == 0) {
-                fsum[warp][(lane >> 2) + 8 * m][0] = ml;
-                fsum[warp][(lane >> 2) + 8 * m][1] = mr;
-            }
+            const float2 a = buf[nat_idx(k)];
+            const float2 bb = buf[nat_idx((SSB_N_FFT - k) & (SSB_N_FFT - 1))];
+            const float lx = a.x + bb.x, ly = a.y - bb.y;      // A + conj(B)
+            const float rx = a.x - bb.x, ry = a.y + bb.y;      // A - conj(B)
+            accl[m] += fast_sqrt(lx * lx + ly * ly);
+            accr[m] += fast_sqrt(rx * rx + ry * ry);
         }
-        if (lane == 0) {                                   // bin 256 is alone in pooled row 64
-            float2 a = buf[nat_idx(256)];
-            fsum[warp][64][0] = fabsf(a.x);
-            fsum[warp][64][1] = fabsf(a.y);
+        if (lane == 0) {                                       // bin 256 is alone in pooled row 64
+            const float2 a = buf[nat_idx(256)];
+            acc64l += fabsf(a.x);
+            acc64r += fabsf(a.y);
         }
-    } else {
-        for (int i = lane; i < SSB_SPEC_ROWS * 2; i += 32) (&fsum[warp][0][0])[i] = 0.f;
+        __syncwarp();                                          // buf is rewritten by the next frame's exchange
+        // slide the sample window by one hop (5 x 32 samples)
+#pragma unroll
+        for (int q = 1; q < 10; ++q) { xl[q] = xl[q + 5]; xr[q] = xr[q + 5]; }
+#pragma unroll
+        for (int u = 0; u < 5; ++u) { xl[10 + u] = nl[u]; xr[10 + u] = nr[u]; }
     }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < SPEC_COLS_PER_CTA * SSB_SPEC_ROWS * 2; idx += SPEC_WARPS * 32) {
-        const int c = idx / (SSB_SPEC_ROWS * 2);
-        const int r = (idx % (SSB_SPEC_ROWS * 2)) >> 1;
-        const int e = idx & 1;
-        const int col = col0 + c;
-        if (col < cols) {
-            float s = (fsum[4 * c][r][e] + fsum[4 * c + 1][r][e]) + (fsum[4 * c + 2][r][e] + fsum[4 * c + 3][r][e]);
-            out[(((long long)env * SSB_SPEC_ROWS + r) * cols + col) * 2 + e] = log1pf(s * (1.0f / 16.0f));
+}
+
+// grid (cols, B); block = ONE warp.  Everything that selects a code path (column index, interior
+// test) derives from blockIdx, so the compiler can prove the warp converged and the shuffles and
+// __syncwarp()s stay single instructions (with several warps per CTA and a per-warp column they
+// were compiled into WARPSYNC.COLLECTIVE sequences).
+template <bool REFLECT>
+__global__ void __launch_bounds__(32, 16)
+spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr, int n_frames, int cols,
+                   float* __restrict__ out, const float2* __restrict__ tw,
+                   const float* __restrict__ window, int dbg) {
+    __shared__ float2 xbuf[SPEC_BUF];
+    const int lane = threadIdx.x;
+    const int col = blockIdx.x;
+    const int env = blockIdx.y;
+    const float* __restrict__ yl = wave + (long long)env * 2 * wave_stride;
+    const float* __restrict__ yr = yl + wave_stride;
+    // every x_j, j = 1..29, in range and all four frames real => no padding logic at all
+    const int first = col * SSB_POOL * SSB_HOP - SSB_N_FFT / 2;
+    const bool interior = first + 32 >= 0 && first + 32 * 30 <= sr && col * SSB_POOL + SSB_POOL <= n_frames;
+    float accl[8], accr[8], acc64l = 0.f, acc64r = 0.f;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) { accl[m] = 0.f; accr[m] = 0.f; }
+    if (interior)
+        spec_column<REFLECT, true>(yl, yr, sr, n_frames, col, lane, xbuf, tw, window, accl, accr, acc64l, acc64r, dbg);
+    else
+        spec_column<REFLECT, false>(yl, yr, sr, n_frames, col, lane, xbuf, tw, window, accl, accr, acc64l, acc64r, dbg);
+    // pool 4 adjacent bins (lanes), scale: 0.5 (packing) / 16 (4x4 mean), log1p, store
+    float* __restrict__ o = out + (((long long)env * SSB_SPEC_ROWS) * cols + col) * 2;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        float l = accl[m], r = accr[m];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        if ((lane & 3) == 0) {
+            const int row = (lane >> 2) + 8 * m;
+            *reinterpret_cast<float2*>(o + (long long)row * cols * 2) =
+                make_float2(log1pf(l * (0.5f / 16.0f)), log1pf(r * (0.5f / 16.0f)));
         }
     }
+    if (lane == 0)
+        *reinterpret_cast<float2*>(o + (long long)64 * cols * 2) =
+            make_float2(log1pf(acc64l * (1.0f / 16.0f)), log1pf(acc64r * (1.0f / 16.0f)));
 }
 
 // ---------------------------------------------------------------------------
@@ -348,24 +418,26 @@ static int log2_supported(int l) {
 template <int LOG2N>
 static int setup_smem_attrs() {
     using P = FftPlan<LOG2N>;
-    const int bytes = P::SMEM_ELEMS * (int)sizeof(float2);
+    const int bytes = (P::SMEM_ELEMS + P::TW_SMALL_ELEMS) * (int)sizeof(float2);
     cudaError_t e = cudaFuncSetAttribute(fwd_rir_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fwd_src_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mac_ifft_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e == cudaSuccess ? 0 : -1;
 }
 
-// twiddle table of FftPlan<LOG2N>: pass p, [s-1][j] = exp(-2 pi i j s / (16 stride(p))), rounded from double
+// twiddle table of FftPlan<LOG2N>: pass p, rows e in {1,2,3,4,8,12}: [row][j] = exp(-2 pi i j e / (16 stride(p))),
+// computed in double and rounded once
 template <int LOG2N>
 static cudaError_t upload_twiddles(ssb_ctx* ctx) {
     using P = FftPlan<LOG2N>;
+    static const int kExp[6] = {1, 2, 3, 4, 8, 12};
     std::vector<float2> h(P::TW_ELEMS);
     for (int p = 0; p < P::NPASS; ++p) {
         const int st = P::stride(p);
-        for (int s = 1; s < 16; ++s)
+        for (int row = 0; row < 6; ++row)
             for (int j = 0; j < st; ++j) {
-                const double a = -2.0 * M_PI * (double)j * (double)s / (16.0 * (double)st);
-                h[P::tw_offset(p) + (s - 1) * st + j] = make_float2((float)cos(a), (float)sin(a));
+                const double a = -2.0 * M_PI * (double)j * (double)kExp[row] / (16.0 * (double)st);
+                h[P::tw_offset(p) + row * st + j] = make_float2((float)cos(a), (float)sin(a));
             }
     }
     cudaError_t e = cudaMalloc(&ctx->tw[LOG2N], h.size() * sizeof(float2));
@@ -417,6 +489,12 @@ extern "C" void ssb_destroy(ssb_ctx* ctx) {
     for (int l = 0; l < 16; ++l)
         if (ctx->tw[l]) cudaFree(ctx->tw[l]);
     if (ctx->window) cudaFree(ctx->window);
+    if (ctx->s_h2d) {
+        cudaStreamDestroy(ctx->s_h2d);
+        cudaStreamDestroy(ctx->s_d2h);
+        for (int i = 0; i < 2 * SSB_MAX_CHUNKS + 2; ++i)
+            if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    }
     if (ctx->timed) {
         for (auto& tl : *ctx->timed) { cudaEventDestroy(tl.a); cudaEventDestroy(tl.b); }
         delete ctx->timed;
@@ -426,6 +504,12 @@ extern "C" void ssb_destroy(ssb_ctx* ctx) {
 
 extern "C" const char* ssb_last_error(const ssb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" int64_t ssb_launch_count(const ssb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ssb_set_debug(ssb_ctx* ctx, int flags) {
+    if (!ctx) return SSB_E_INVALID_ARG;
+    ctx->debug = flags;
+    return SSB_OK;
+}
 
 extern "C" int ssb_set_kernel_timing(ssb_ctx* ctx, int enable) {
     if (!ctx) return SSB_E_INVALID_ARG;
@@ -487,7 +571,7 @@ static cudaError_t launch_src(ssb_ctx* ctx, const float* d_src, int S, int64_t m
     using P = FftPlan<LOG2N>;
     {
         LaunchTimer lt(ctx, K_FWD_SRC, st);
-        fwd_src_kernel<LOG2N><<<nw, P::T, P::SMEM_ELEMS * sizeof(float2), st>>>(d_src, S, (long long)m0, wrap, wofs, d_x, ctx->tw[LOG2N]);
+        fwd_src_kernel<LOG2N><<<nw, P::T, (P::SMEM_ELEMS + P::TW_SMALL_ELEMS) * sizeof(float2), st>>>(d_src, S, (long long)m0, wrap, wofs, d_x, ctx->tw[LOG2N]);
     }
     return cudaGetLastError();
 }
@@ -513,7 +597,7 @@ template <int LOG2N>
 static cudaError_t launch_conv(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs, const float* d_rir_bank,
                                const void* d_xpool, void* d_h, float* d_wave, int64_t wave_stride, cudaStream_t st) {
     using P = FftPlan<LOG2N>;
-    const size_t smem = P::SMEM_ELEMS * sizeof(float2);
+    const size_t smem = (P::SMEM_ELEMS + P::TW_SMALL_ELEMS) * sizeof(float2);
     dim3 g1(plan->max_parts * plan->n_terms, B);
     {
         LaunchTimer lt(ctx, K_FWD_RIR, st);
@@ -522,12 +606,12 @@ static cudaError_t launch_conv(ssb_ctx* ctx, const ssb_plan* plan, int B, const 
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    dim3 g2(plan->n_blocks, B);
+    dim3 g2(B, plan->n_blocks);
     {
         LaunchTimer lt(ctx, K_MAC_IFFT, st);
         mac_ifft_kernel<LOG2N><<<g2, P::T, smem, st>>>(d_reqs, (const float2*)d_xpool, (const float2*)d_h, plan->max_parts,
                                                        plan->n_terms, (long long)plan->h_elems_per_env, d_wave,
-                                                       (long long)wave_stride, plan->sr, ctx->tw[LOG2N]);
+                                                       (long long)wave_stride, plan->sr, ctx->tw[LOG2N], ctx->debug);
     }
     return cudaGetLastError();
 }
@@ -577,11 +661,15 @@ extern "C" int ssb_spectrogram_batch(ssb_ctx* ctx, int B, const float* d_wave, i
         SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_spectrogram_batch: bad arguments (B=%d sr=%d pad_mode=%d)", B, sr, pad_mode);
     const int frames = 1 + sr / SSB_HOP;
     const int cols = ssb_spec_cols(sr);
-    dim3 g((cols + SPEC_COLS_PER_CTA - 1) / SPEC_COLS_PER_CTA, B);
+    dim3 g(cols, B);
     {
         LaunchTimer lt(ctx, K_SPECTROGRAM, (cudaStream_t)stream);
-        spectrogram_kernel<<<g, SPEC_WARPS * 32, 0, (cudaStream_t)stream>>>(d_wave, (long long)wave_stride, sr, frames, cols,
-                                                                           pad_mode, d_spec, ctx->tw[9], ctx->window);
+        if (pad_mode == SSB_PAD_REFLECT)
+            spectrogram_kernel<true><<<g, 32, 0, (cudaStream_t)stream>>>(
+                d_wave, (long long)wave_stride, sr, frames, cols, d_spec, ctx->tw[9], ctx->window, ctx->debug);
+        else
+            spectrogram_kernel<false><<<g, 32, 0, (cudaStream_t)stream>>>(
+                d_wave, (long long)wave_stride, sr, frames, cols, d_spec, ctx->tw[9], ctx->window, ctx->debug);
     }
     SSB_CUDA(ctx, cudaGetLastError());
     return SSB_OK;
@@ -595,25 +683,87 @@ extern "C" int ssb_render_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const
     return ssb_spectrogram_batch(ctx, B, d_wave, wave_stride, plan->sr, pad_mode, d_spec, stream);
 }
 
+// Host-buffer entry.  n_chunks > 1 pipelines the batch: chunk c+1's H2D copy (copy stream) overlaps
+// chunk c's kernels (caller's stream) and chunk c-1's D2H copy (second copy stream); PCIe is full
+// duplex, so a step costs about max(H2D, kernels, D2H) instead of their sum.
 extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* h_reqs, const float* h_rir,
                                      int64_t rir_bytes, float* d_rir_staging, ssb_req* d_reqs_staging, const void* d_xpool,
                                      void* d_hscratch, float* d_wave, int64_t wave_stride, int pad_mode, float* d_spec,
-                                     float* h_spec, float* h_wave, void* stream) {
+                                     float* h_spec, float* h_wave, int n_chunks, void* stream) {
     int rc = check_plan(ctx, plan);
     if (rc) return rc;
-    if (B <= 0 || !h_reqs || !h_rir || rir_bytes <= 0 || !d_rir_staging || !d_reqs_staging || !h_spec)
+    if (B <= 0 || !h_reqs || !h_rir || rir_bytes <= 0 || !d_rir_staging || !d_reqs_staging || !h_spec || !d_spec ||
+        !d_wave || wave_stride < plan->sr)
         SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_render_batch_host: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    SSB_CUDA(ctx, cudaMemcpyAsync(d_rir_staging, h_rir, (size_t)rir_bytes, cudaMemcpyHostToDevice, st));
-    SSB_CUDA(ctx, cudaMemcpyAsync(d_reqs_staging, h_reqs, (size_t)B * sizeof(ssb_req), cudaMemcpyHostToDevice, st));
-    rc = ssb_render_batch(ctx, plan, B, d_reqs_staging, d_rir_staging, d_xpool, d_hscratch, d_wave, wave_stride, pad_mode,
-                          d_spec, stream);
-    if (rc) return rc;
-    const size_t spec_bytes = (size_t)B * SSB_SPEC_ROWS * ssb_spec_cols(plan->sr) * 2 * sizeof(float);
-    SSB_CUDA(ctx, cudaMemcpyAsync(h_spec, d_spec, spec_bytes, cudaMemcpyDeviceToHost, st));
-    if (h_wave)
-        SSB_CUDA(ctx, cudaMemcpy2DAsync(h_wave, (size_t)plan->sr * sizeof(float), d_wave, (size_t)wave_stride * sizeof(float),
-                                        (size_t)plan->sr * sizeof(float), (size_t)B * 2, cudaMemcpyDeviceToHost, st));
+    const size_t spec_row = (size_t)SSB_SPEC_ROWS * ssb_spec_cols(plan->sr) * 2;      // floats per env
+    if (n_chunks > B) n_chunks = B;
+    if (n_chunks > SSB_MAX_CHUNKS) n_chunks = SSB_MAX_CHUNKS;
+    if (n_chunks <= 1) {
+        SSB_CUDA(ctx, cudaMemcpyAsync(d_rir_staging, h_rir, (size_t)rir_bytes, cudaMemcpyHostToDevice, st));
+        SSB_CUDA(ctx, cudaMemcpyAsync(d_reqs_staging, h_reqs, (size_t)B * sizeof(ssb_req), cudaMemcpyHostToDevice, st));
+        rc = ssb_render_batch(ctx, plan, B, d_reqs_staging, d_rir_staging, d_xpool, d_hscratch, d_wave, wave_stride,
+                              pad_mode, d_spec, stream);
+        if (rc) return rc;
+        SSB_CUDA(ctx, cudaMemcpyAsync(h_spec, d_spec, (size_t)B * spec_row * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (h_wave)
+            SSB_CUDA(ctx, cudaMemcpy2DAsync(h_wave, (size_t)plan->sr * sizeof(float), d_wave,
+                                            (size_t)wave_stride * sizeof(float), (size_t)plan->sr * sizeof(float),
+                                            (size_t)B * 2, cudaMemcpyDeviceToHost, st));
+        return SSB_OK;
+    }
+    if (!ctx->s_h2d) {
+        SSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        SSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * SSB_MAX_CHUNKS + 2; ++i)
+            SSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+    }
+    cudaEvent_t ev_entry = ctx->ev[2 * SSB_MAX_CHUNKS], ev_done = ctx->ev[2 * SSB_MAX_CHUNKS + 1];
+    // copies must not overtake earlier work on the caller's stream that still uses the staging buffers
+    SSB_CUDA(ctx, cudaEventRecord(ev_entry, st));
+    SSB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_entry, 0));
+    SSB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev_entry, 0));
+    SSB_CUDA(ctx, cudaMemcpyAsync(d_reqs_staging, h_reqs, (size_t)B * sizeof(ssb_req), cudaMemcpyHostToDevice, ctx->s_h2d));
+    const int64_t bank_taps = rir_bytes / (int64_t)sizeof(float2);
+    const int per = (B + n_chunks - 1) / n_chunks;
+    int c = 0;
+    for (int e0 = 0; e0 < B; e0 += per, ++c) {
+        const int nb = (B - e0 < per) ? (B - e0) : per;
+        // tap range of the host bank this chunk reads
+        int64_t lo = bank_taps, hi = 0;
+        for (int e = e0; e < e0 + nb; ++e) {
+            if (h_reqs[e].flags & SSB_FLAG_SILENT) continue;
+            for (int term = 0; term < plan->n_terms; ++term) {
+                const ssb_conv_term& ct = h_reqs[e].term[term];
+                if (ct.rir_taps <= 0) continue;
+                if (ct.rir_offset < 0 || ct.rir_offset + ct.rir_taps > bank_taps)
+                    SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_render_batch_host: request %d reads outside the host RIR buffer", e);
+                if (ct.rir_offset < lo) lo = ct.rir_offset;
+                if (ct.rir_offset + ct.rir_taps > hi) hi = ct.rir_offset + ct.rir_taps;
+            }
+        }
+        if (hi > lo)
+            SSB_CUDA(ctx, cudaMemcpyAsync(d_rir_staging + 2 * lo, h_rir + 2 * lo, (size_t)(hi - lo) * sizeof(float2),
+                                          cudaMemcpyHostToDevice, ctx->s_h2d));
+        SSB_CUDA(ctx, cudaEventRecord(ctx->ev[2 * c], ctx->s_h2d));
+        SSB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[2 * c], 0));
+        rc = ssb_render_batch(ctx, plan, nb, d_reqs_staging + e0, d_rir_staging, d_xpool,
+                              (float2*)d_hscratch + (size_t)e0 * plan->h_elems_per_env, d_wave + (size_t)e0 * 2 * wave_stride,
+                              wave_stride, pad_mode, d_spec + (size_t)e0 * spec_row, stream);
+        if (rc) return rc;
+        SSB_CUDA(ctx, cudaEventRecord(ctx->ev[2 * c + 1], st));
+        SSB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev[2 * c + 1], 0));
+        SSB_CUDA(ctx, cudaMemcpyAsync(h_spec + (size_t)e0 * spec_row, d_spec + (size_t)e0 * spec_row,
+                                      (size_t)nb * spec_row * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (h_wave)
+            SSB_CUDA(ctx, cudaMemcpy2DAsync(h_wave + (size_t)e0 * 2 * plan->sr, (size_t)plan->sr * sizeof(float),
+                                            d_wave + (size_t)e0 * 2 * wave_stride, (size_t)wave_stride * sizeof(float),
+                                            (size_t)plan->sr * sizeof(float), (size_t)nb * 2, cudaMemcpyDeviceToHost,
+                                            ctx->s_d2h));
+    }
+    // the caller's stream completes when the last D2H copy has landed
+    SSB_CUDA(ctx, cudaEventRecord(ev_done, ctx->s_d2h));
+    SSB_CUDA(ctx, cudaStreamWaitEvent(st, ev_done, 0));
     return SSB_OK;
 }
 

@@ -306,9 +306,9 @@ class BatchedAudioRenderer:
         return spec
 
     # --------------------------------------------------------- host-buffer path
-    def make_host_session(self, n: int, taps: int, want_wave: bool = False):
-        """Pinned host buffers + device staging for ``render_host`` (the e2e path)."""
-        return HostSession(self, n, taps, want_wave)
+    def make_host_session(self, n: int, taps: int, want_wave: bool = False, n_chunks: int = 4):
+        """Pinned host buffers + device staging for the host-buffer entry (the e2e path)."""
+        return HostSession(self, n, taps, want_wave, n_chunks)
 
 
 class HostSession:
@@ -316,8 +316,8 @@ class HostSession:
     host memory, rendered, and the spectrograms (optionally waveforms) are copied back --
     what the reference's per-env numpy API hands over and gets back."""
 
-    def __init__(self, r: BatchedAudioRenderer, n: int, taps: int, want_wave: bool):
-        self.r, self.n, self.taps = r, n, taps
+    def __init__(self, r: BatchedAudioRenderer, n: int, taps: int, want_wave: bool, n_chunks: int = 4):
+        self.r, self.n, self.taps, self.n_chunks = r, n, taps, n_chunks
         self.h_rir = torch.empty((n, taps, 2), dtype=torch.float32).pin_memory()
         self.h_spec = torch.empty((n,) + r.spec_shape, dtype=torch.float32).pin_memory()
         self.h_wave = torch.empty((n, 2, r.sr), dtype=torch.float32).pin_memory() if want_wave else None
@@ -354,5 +354,6 @@ class HostSession:
             r.ctx.handle, C.byref(r.plan), self.n, self.h_reqs.data_ptr(), self.h_rir.data_ptr(),
             self.h_rir.numel() * 4, self.d_rir.data_ptr(), self.d_reqs.data_ptr(), r._xpool.data_ptr(),
             hs.data_ptr(), wave.data_ptr(), r.sr, r.pad_mode, self.d_spec.data_ptr(), self.h_spec.data_ptr(),
-            self.h_wave.data_ptr() if self.h_wave is not None else None, r._stream()), "ssb_render_batch_host")
+            self.h_wave.data_ptr() if self.h_wave is not None else None, self.n_chunks, r._stream()),
+            "ssb_render_batch_host")
         return self.h_spec

@@ -205,21 +205,27 @@ def test_full_size_c2_properties():
     assert np.array_equal(spec2.cpu().numpy(), spec_h[perm])
 
 
-def test_host_session_e2e():
-    sr, L, B = 16000, 6000, 8
+@pytest.mark.parametrize("n_chunks", [1, 3, 4, 32])
+def test_host_session_e2e(n_chunks):
+    """Host-buffer entry, serial and pipelined (chunked H2D / kernels / D2H on separate streams)."""
+    sr, L, B = 16000, 6000, 11
     r = renderer(sr, L)
     src = make_source(3, sr)
     sid = r.add_source(src)
-    hs = r.make_host_session(B, L, want_wave=True)
+    hs = r.make_host_session(B, L, want_wave=True, n_chunks=n_chunks)
     rirs = np.stack([make_rir(50 + i, L) for i in range(B)])
-    hs.h_rir.numpy()[:] = rirs
-    hs.set_requests(sid)
-    hs.run()
+    taps = [L, L, 0, 1, 4097, L, L, 17, L, L, L]
+    silent = [i == 4 for i in range(B)]
+    for rep in range(3):                               # back-to-back steps reuse the staging buffers
+        rirs = np.roll(rirs, 1, axis=0)
+        hs.h_rir.numpy()[:] = rirs
+        hs.set_requests(sid, silent=silent, taps=taps)
+        hs.run()
     torch.cuda.synchronize()
     for i in range(B):
-        w_ref, s_ref = ao.render_frame(src, rirs[i], sr)
+        w_ref, s_ref = ao.render_frame(src, rirs[i][:taps[i]], sr, silent=silent[i])
         check_wave(hs.h_wave[i].numpy(), w_ref)
-        check_spec(hs.h_spec[i].numpy(), s_ref)
+        check_spec(hs.h_spec[i].numpy(), s_ref.astype(np.float32))
 
 
 def test_error_reporting():
