@@ -104,15 +104,23 @@ int64_t ssb_launch_count(const ssb_ctx* ctx);
 #define SSB_K_MAC_IFFT 1
 #define SSB_K_SPECTROGRAM 2
 #define SSB_K_FWD_SRC 3
-#define SSB_N_KERNELS 4
+#define SSB_K_MAC_BINS 4
+#define SSB_N_KERNELS 5
 int ssb_set_kernel_timing(ssb_ctx* ctx, int enable);
 int ssb_get_kernel_timing(ssb_ctx* ctx, double* ms_sum /*[SSB_N_KERNELS]*/, int64_t* counts /*[SSB_N_KERNELS]*/);
+
+/* Convolution schedule: 0 (default) = per-bin partition sums (mac_bins_kernel) then inverse FFTs;
+ * 1 = partition sums fused into the inverse-FFT kernel (re-reads every RIR partition per block). */
+int ssb_set_conv_mode(ssb_ctx* ctx, int mode);
+/* ssb_render_batch splits the batch over n (1..8) internal streams forked from / joined to the
+ * caller's stream, so kernel tails and memory- vs compute-bound kernels of different sub-batches overlap */
+int ssb_set_streams(ssb_ctx* ctx, int n);
 
 /* Profiling only: ablation switches (1 skip the spectrum MAC, 2 skip the inverse FFT, 4 skip the
  * waveform loads of the spectrogram kernel, 8 skip its FFT).  Results are wrong when non-zero. */
 int ssb_set_debug(ssb_ctx* ctx, int flags);
 
-/* Fill a plan.  log2n = 0 picks the default (13). */
+/* Fill a plan.  log2n = 0 picks the default (12). */
 int ssb_make_plan(ssb_ctx* ctx, int sr, int max_taps, int n_terms, int log2n, ssb_plan* plan);
 
 /* spectrogram geometry: frames = 1 + sr/160, cols = ceil(frames/4) */

@@ -6,6 +6,8 @@ from soundspaces_b200 import AudioRequest, BatchedAudioRenderer
 sr, L, B = 44100, 16384, 128
 log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 13
 r = BatchedAudioRenderer(sr, L, log2n=log2n)
+r.set_conv_mode(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+r.lib.ssb_set_sub_batch(r.ctx.handle, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
 sid = r.add_source(make_source(7, sr))
 rng = np.random.default_rng(0)
 bank = torch.from_numpy((rng.standard_normal((8 * B, L, 2)) * 0.1).astype(np.float32)).cuda()
@@ -18,6 +20,6 @@ def run(flags, n=100):
     r.ctx.set_kernel_timing(True)
     for i in range(n): r.execute(batches[i % 8])
     kt = r.ctx.get_kernel_timing(); r.ctx.set_kernel_timing(False)
-    return {k: round(v[0] / max(1, v[1]) * 1e3, 1) for k, v in kt.items() if v[1]}
+    return {k: round(v[0] / n * 1e3, 1) for k, v in kt.items() if v[1]}, 'launches/step', sum(v[1] for v in kt.values()) / n
 for flags, name in [(0, "full"), (1, "no MAC"), (2, "no IFFT"), (3, "no MAC no IFFT"), (4, "spec: no loads"), (8, "spec: no FFT"), (12, "spec: no loads no FFT")]:
     print(f"{name:24s}", run(flags), flush=True)

@@ -14,7 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libssb200.so")
+LIB_PATH = os.environ.get("SSB200_LIB", os.path.join(_HERE, "libssb200.so"))   # override: A/B builds while tuning
 SOURCES = [os.path.join(_HERE, "csrc", "ssb200.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "fft16.cuh"), os.path.join(ROOT, "include", "ssb200.h")]
 
@@ -43,6 +43,8 @@ EXPORTS = {
     "ssb_destroy": (None, [C.c_void_p]),
     "ssb_last_error": (C.c_char_p, [C.c_void_p]),
     "ssb_launch_count": (C.c_int64, [C.c_void_p]),
+    "ssb_set_conv_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssb_set_streams": (C.c_int, [C.c_void_p, C.c_int]),
     "ssb_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "ssb_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ssb_get_kernel_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -126,15 +128,15 @@ class Context:
         self.check(self.lib.ssb_make_plan(self.handle, sr, max_taps, n_terms, log2n, C.byref(plan)), "ssb_make_plan")
         return plan
 
-    KERNEL_NAMES = ("fwd_rir_kernel", "mac_ifft_kernel", "spectrogram_kernel", "fwd_src_kernel")
+    KERNEL_NAMES = ("fwd_rir_kernel", "mac_ifft_kernel", "spectrogram_kernel", "fwd_src_kernel", "mac_bins_kernel")
 
     def set_kernel_timing(self, enable):
         self.check(self.lib.ssb_set_kernel_timing(self.handle, int(bool(enable))), "ssb_set_kernel_timing")
 
     def get_kernel_timing(self):
         """{kernel: (summed ms, launches)} since the last call (synchronises)."""
-        ms = (C.c_double * 4)()
-        cnt = (C.c_int64 * 4)()
+        ms = (C.c_double * 5)()
+        cnt = (C.c_int64 * 5)()
         self.check(self.lib.ssb_get_kernel_timing(self.handle, ms, cnt), "ssb_get_kernel_timing")
         return {n: (ms[i], cnt[i]) for i, n in enumerate(self.KERNEL_NAMES)}
 

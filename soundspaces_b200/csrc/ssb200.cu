@@ -23,8 +23,9 @@ using namespace ssb;
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
-enum { K_FWD_RIR = 0, K_MAC_IFFT = 1, K_SPECTROGRAM = 2, K_FWD_SRC = 3, K_COUNT = SSB_N_KERNELS };
+enum { K_FWD_RIR = 0, K_MAC_IFFT = 1, K_SPECTROGRAM = 2, K_FWD_SRC = 3, K_MAC_BINS = 4, K_COUNT = SSB_N_KERNELS };
 #define SSB_MAX_CHUNKS 32
+#define SSB_MAX_STREAMS 8
 struct TimedLaunch { int kernel; cudaEvent_t a, b; };
 
 struct ssb_ctx {
@@ -37,6 +38,16 @@ struct ssb_ctx {
     int timing;
     cudaStream_t s_h2d, s_d2h;                     // copy streams of the pipelined host entry
     cudaEvent_t ev[2 * SSB_MAX_CHUNKS + 2];
+    // last two staging buffers written by the copy stream and the event after the kernels that read them
+    const void* stage_ptr[2];
+    cudaEvent_t stage_done[2];
+    int stage_next;
+    float2* yscratch;                              // [env][block][N] partition sums (transposed MAC)
+    size_t yscratch_elems;
+    int conv_mode;       // 0: mac_bins + ifft (default), 1: fused mac_ifft
+    int n_streams;       // internal compute streams of ssb_render_batch (1 = caller's stream only)
+    cudaStream_t s_comp[SSB_MAX_STREAMS];
+    cudaEvent_t ev_comp[SSB_MAX_STREAMS], ev_fork;
     int debug;           // ablation switches for profiling (ssb_set_debug); 0 in production
     std::vector<TimedLaunch>* timed;
     char err[512];
@@ -156,10 +167,79 @@ fwd_src_kernel(const float* __restrict__ src, int S, long long m0, int wrap, int
 }
 
 // ---------------------------------------------------------------------------
+// "transposed" multiply-accumulate: one thread per (env, spectrum slot) forms ALL the block sums
+//   Y[b][s] = sum_p X[b - p + wofs][s] * H[p][s]
+// so every H value crosses the L2->SM link once (the fused loop in mac_ifft_kernel re-reads each
+// partition for every block: 4.9 MB per env at config 2 against 0.26 + 0.70 MB here); repeated
+// touches of the same slot column are L1 hits.  grid (N / 256, B); block 256.
+// ---------------------------------------------------------------------------
+template <int LOG2N, int NPMAX, int NBMAX>
+__global__ void __launch_bounds__(256)
+mac_bins_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpool, const float2* __restrict__ H,
+                int max_parts, int n_terms, long long h_elems_per_env, float2* __restrict__ Y, int n_blocks, int sr) {
+    using P = FftPlan<LOG2N>;
+    constexpr int PART = P::N / 2;
+    const int env = blockIdx.y;
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    const ssb_req& rq = reqs[env];
+    if (rq.flags & SSB_FLAG_SILENT) return;
+    const int nvalid = min(rq.out_samples, sr);
+    const int nblk = (nvalid + PART - 1) / PART;
+    float2* __restrict__ yo = Y + (long long)env * n_blocks * P::N + s;
+    bool first = true;                                          // first term stores, later terms accumulate into Y
+    for (int term = 0; term < n_terms; ++term) {
+        const ssb_conv_term& ct = rq.term[term];
+        if (ct.rir_taps <= 0) continue;
+        const int nparts = min((ct.rir_taps + PART - 1) / PART, max_parts);
+        const float2* __restrict__ hp = H + (long long)env * h_elems_per_env + (long long)term * max_parts * P::N + s;
+        const float2* __restrict__ xp = xpool + ct.x_offset + s;
+        if (ct.x_wofs == 0 && nparts <= NPMAX && nblk <= NBMAX && ct.x_nw >= nblk) {
+            // fast path (clip starts at offset 0): every operand is loaded exactly once, up front
+            float2 h[NPMAX], x[NBMAX];
+#pragma unroll
+            for (int p = 0; p < NPMAX; ++p) h[p] = p < nparts ? hp[(long long)p * P::N] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < NBMAX; ++w) x[w] = w < nblk ? __ldg(xp + (long long)w * P::N) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int b = 0; b < NBMAX; ++b) {
+                if (b < nblk) {
+                    float2 acc = first ? make_float2(0.f, 0.f) : yo[(long long)b * P::N];
+#pragma unroll
+                    for (int p = 0; p < NPMAX; ++p) {
+                        if (p <= b) {                           // window b - p >= 0; h[p] is 0 beyond nparts
+                            acc.x = fmaf(x[b - p].x, h[p].x, fmaf(-x[b - p].y, h[p].y, acc.x));
+                            acc.y = fmaf(x[b - p].x, h[p].y, fmaf(x[b - p].y, h[p].x, acc.y));
+                        }
+                    }
+                    yo[(long long)b * P::N] = acc;
+                }
+            }
+        } else {
+            // general path: arbitrary window offset / partition count; repeated touches are L1 hits
+            for (int b = 0; b < nblk; ++b) {
+                float2 acc = first ? make_float2(0.f, 0.f) : yo[(long long)b * P::N];
+                const int p_lo = max(0, b + ct.x_wofs - (ct.x_nw - 1));
+                const int p_hi = min(nparts - 1, b + ct.x_wofs);
+                for (int p = p_lo; p <= p_hi; ++p) {
+                    const float2 h = hp[(long long)p * P::N];
+                    const float2 x = __ldg(xp + (long long)(b - p + ct.x_wofs) * P::N);
+                    acc.x = fmaf(x.x, h.x, fmaf(-x.y, h.y, acc.x));
+                    acc.y = fmaf(x.x, h.y, fmaf(x.y, h.x, acc.y));
+                }
+                yo[(long long)b * P::N] = acc;
+            }
+        }
+        first = false;
+    }
+    if (first)                                                  // no term had taps: the inverse-FFT kernel writes zeros itself
+        return;
+}
+
+// ---------------------------------------------------------------------------
 // multiply-accumulate over partitions + inverse FFT + emit
 // grid (B, n_blocks); block T.
 // ---------------------------------------------------------------------------
-template <int LOG2N>
+template <int LOG2N, bool FROM_Y>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::T)
 mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpool,
                 const float2* __restrict__ H, int max_parts, int n_terms, long long h_elems_per_env,
@@ -192,6 +272,12 @@ mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
         return;
     }
     float2 acc[16];
+    if constexpr (FROM_Y) {
+        // the partition sums were formed per bin by mac_bins_kernel; H here is its output Y[env][b][N]
+        const float2* __restrict__ yp = H + ((long long)env * gridDim.y + b) * P::N + t;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = (dbg & 1) ? make_float2(0.f, 0.f) : yp[i * P::T];
+    } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = make_float2(0.f, 0.f);
     for (int term = 0; term < n_terms; ++term) {
@@ -215,6 +301,7 @@ mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
                 acc[i].y = fmaf(x[i].x, h[i].y, fmaf(x[i].y, h[i].x, acc[i].y));
             }
         }
+    }
     }
     stage_small_twiddles<LOG2N>(stw, tw, t);
     __syncthreads();
@@ -332,8 +419,11 @@ __device__ __forceinline__ void spec_column(const float* __restrict__ yl, const 
 // test) derives from blockIdx, so the compiler can prove the warp converged and the shuffles and
 // __syncwarp()s stay single instructions (with several warps per CTA and a per-warp column they
 // were compiled into WARPSYNC.COLLECTIVE sequences).
+#ifndef SPEC_MIN_BLOCKS
+#define SPEC_MIN_BLOCKS 16
+#endif
 template <bool REFLECT>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(32, SPEC_MIN_BLOCKS)
 spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr, int n_frames, int cols,
                    float* __restrict__ out, const float2* __restrict__ tw,
                    const float* __restrict__ window, int dbg) {
@@ -421,7 +511,8 @@ static int setup_smem_attrs() {
     const int bytes = (P::SMEM_ELEMS + P::TW_SMALL_ELEMS) * (int)sizeof(float2);
     cudaError_t e = cudaFuncSetAttribute(fwd_rir_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fwd_src_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mac_ifft_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mac_ifft_kernel<LOG2N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mac_ifft_kernel<LOG2N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e == cudaSuccess ? 0 : -1;
 }
 
@@ -461,6 +552,7 @@ extern "C" int ssb_create(int device, ssb_ctx** out) {
     SSB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) SSB_FAIL(ctx, SSB_E_CUDA, "device %d is sm_%d%d; libssb200 is built for sm_100a only", device, prop.major, prop.minor);
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->n_streams = 2;
     {
         cudaError_t e = cudaSuccess;
         if (e == cudaSuccess) e = upload_twiddles<9>(ctx);
@@ -489,11 +581,18 @@ extern "C" void ssb_destroy(ssb_ctx* ctx) {
     for (int l = 0; l < 16; ++l)
         if (ctx->tw[l]) cudaFree(ctx->tw[l]);
     if (ctx->window) cudaFree(ctx->window);
+    if (ctx->yscratch) cudaFree(ctx->yscratch);
+    if (ctx->s_comp[0]) {
+        for (int i = 0; i < SSB_MAX_STREAMS; ++i) { cudaStreamDestroy(ctx->s_comp[i]); cudaEventDestroy(ctx->ev_comp[i]); }
+        cudaEventDestroy(ctx->ev_fork);
+    }
     if (ctx->s_h2d) {
         cudaStreamDestroy(ctx->s_h2d);
         cudaStreamDestroy(ctx->s_d2h);
         for (int i = 0; i < 2 * SSB_MAX_CHUNKS + 2; ++i)
             if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+        for (int i = 0; i < 2; ++i)
+            if (ctx->stage_done[i]) cudaEventDestroy(ctx->stage_done[i]);
     }
     if (ctx->timed) {
         for (auto& tl : *ctx->timed) { cudaEventDestroy(tl.a); cudaEventDestroy(tl.b); }
@@ -504,6 +603,18 @@ extern "C" void ssb_destroy(ssb_ctx* ctx) {
 
 extern "C" const char* ssb_last_error(const ssb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" int64_t ssb_launch_count(const ssb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ssb_set_conv_mode(ssb_ctx* ctx, int mode) {
+    if (!ctx || (mode != 0 && mode != 1)) return SSB_E_INVALID_ARG;
+    ctx->conv_mode = mode;
+    return SSB_OK;
+}
+
+extern "C" int ssb_set_streams(ssb_ctx* ctx, int n) {
+    if (!ctx || n < 1 || n > SSB_MAX_STREAMS) return SSB_E_INVALID_ARG;
+    ctx->n_streams = n;
+    return SSB_OK;
+}
 
 extern "C" int ssb_set_debug(ssb_ctx* ctx, int flags) {
     if (!ctx) return SSB_E_INVALID_ARG;
@@ -541,7 +652,7 @@ extern "C" int ssb_spec_cols(int sr) {
 
 extern "C" int ssb_make_plan(ssb_ctx* ctx, int sr, int max_taps, int n_terms, int log2n, ssb_plan* plan) {
     if (!ctx || !plan) return SSB_E_INVALID_ARG;
-    if (log2n == 0) log2n = 13;
+    if (log2n == 0) log2n = 12;
     if (log2n < 12 || !log2_supported(log2n)) SSB_FAIL(ctx, SSB_E_INVALID_ARG, "log2n %d unsupported (12, 13, 14)", log2n);
     if (sr < SSB_N_FFT || max_taps < 0 || n_terms < 1 || n_terms > 2)
         SSB_FAIL(ctx, SSB_E_INVALID_ARG, "bad plan arguments sr=%d max_taps=%d n_terms=%d", sr, max_taps, n_terms);
@@ -594,8 +705,9 @@ extern "C" int ssb_source_windows(ssb_ctx* ctx, const ssb_plan* plan, const floa
 }
 
 template <int LOG2N>
-static cudaError_t launch_conv(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs, const float* d_rir_bank,
-                               const void* d_xpool, void* d_h, float* d_wave, int64_t wave_stride, cudaStream_t st) {
+static cudaError_t launch_conv_sub(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs, const float* d_rir_bank,
+                                   const void* d_xpool, void* d_h, float2* y, float* d_wave, int64_t wave_stride,
+                                   cudaStream_t st) {
     using P = FftPlan<LOG2N>;
     const size_t smem = (P::SMEM_ELEMS + P::TW_SMALL_ELEMS) * sizeof(float2);
     dim3 g1(plan->max_parts * plan->n_terms, B);
@@ -607,13 +719,53 @@ static cudaError_t launch_conv(ssb_ctx* ctx, const ssb_plan* plan, int B, const 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 g2(B, plan->n_blocks);
-    {
+    if (ctx->conv_mode == 0) {
+        {
+            LaunchTimer lt(ctx, K_MAC_BINS, st);
+            mac_bins_kernel<LOG2N, 8, 24><<<dim3(P::N / 256, B), 256, 0, st>>>(
+                d_reqs, (const float2*)d_xpool, (const float2*)d_h, plan->max_parts, plan->n_terms,
+                (long long)plan->h_elems_per_env, y, plan->n_blocks, plan->sr);
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
         LaunchTimer lt(ctx, K_MAC_IFFT, st);
-        mac_ifft_kernel<LOG2N><<<g2, P::T, smem, st>>>(d_reqs, (const float2*)d_xpool, (const float2*)d_h, plan->max_parts,
-                                                       plan->n_terms, (long long)plan->h_elems_per_env, d_wave,
-                                                       (long long)wave_stride, plan->sr, ctx->tw[LOG2N], ctx->debug);
+        mac_ifft_kernel<LOG2N, true><<<g2, P::T, smem, st>>>(d_reqs, (const float2*)d_xpool, y, plan->max_parts,
+                                                             plan->n_terms, (long long)plan->h_elems_per_env, d_wave,
+                                                             (long long)wave_stride, plan->sr, ctx->tw[LOG2N], ctx->debug);
+    } else {
+        LaunchTimer lt(ctx, K_MAC_IFFT, st);
+        mac_ifft_kernel<LOG2N, false><<<g2, P::T, smem, st>>>(d_reqs, (const float2*)d_xpool, (const float2*)d_h, plan->max_parts,
+                                                              plan->n_terms, (long long)plan->h_elems_per_env, d_wave,
+                                                              (long long)wave_stride, plan->sr, ctx->tw[LOG2N], ctx->debug);
     }
     return cudaGetLastError();
+}
+
+// partition-sum scratch Y[B][n_blocks][N] (mode 0), owned by the context
+static cudaError_t ensure_yscratch(ssb_ctx* ctx, const ssb_plan* plan, int B, cudaStream_t st) {
+    if (ctx->conv_mode != 0) return cudaSuccess;
+    const size_t need = (size_t)B * plan->n_blocks * ((size_t)1 << plan->log2n);
+    if (need <= ctx->yscratch_elems) return cudaSuccess;
+    if (ctx->yscratch) {
+        cudaDeviceSynchronize();
+        cudaFree(ctx->yscratch);
+        ctx->yscratch = nullptr;
+        ctx->yscratch_elems = 0;
+    }
+    (void)st;
+    cudaError_t e = cudaMalloc(&ctx->yscratch, need * sizeof(float2));
+    if (e == cudaSuccess) ctx->yscratch_elems = need;
+    return e;
+}
+
+static cudaError_t launch_conv_any(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs, const float* d_rir_bank,
+                                   const void* d_xpool, void* d_h, float2* y, float* d_wave, int64_t wave_stride,
+                                   cudaStream_t st) {
+    switch (plan->log2n) {
+        case 12: return launch_conv_sub<12>(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_h, y, d_wave, wave_stride, st);
+        case 13: return launch_conv_sub<13>(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_h, y, d_wave, wave_stride, st);
+        default: return launch_conv_sub<14>(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_h, y, d_wave, wave_stride, st);
+    }
 }
 
 extern "C" int ssb_convolve_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs,
@@ -628,13 +780,8 @@ extern "C" int ssb_convolve_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, con
     if (((uintptr_t)d_rir_bank & 7) || ((uintptr_t)d_xpool & 7) || ((uintptr_t)d_hscratch & 7))
         SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_convolve_batch: rir bank / spectra must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e;
-    switch (plan->log2n) {
-        case 12: e = launch_conv<12>(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_hscratch, d_wave, wave_stride, st); break;
-        case 13: e = launch_conv<13>(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_hscratch, d_wave, wave_stride, st); break;
-        default: e = launch_conv<14>(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_hscratch, d_wave, wave_stride, st); break;
-    }
-    SSB_CUDA(ctx, e);
+    SSB_CUDA(ctx, ensure_yscratch(ctx, plan, B, st));
+    SSB_CUDA(ctx, launch_conv_any(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_hscratch, ctx->yscratch, d_wave, wave_stride, st));
     return SSB_OK;
 }
 
@@ -652,8 +799,16 @@ extern "C" int ssb_crossfade_batch(ssb_ctx* ctx, int B, const float* d_prev, flo
     return SSB_OK;
 }
 
+static int spectrogram_checked(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int pad_mode,
+                               float* d_spec, cudaStream_t st);
+
 extern "C" int ssb_spectrogram_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int pad_mode,
                                      float* d_spec, void* stream) {
+    return spectrogram_checked(ctx, B, d_wave, wave_stride, sr, pad_mode, d_spec, (cudaStream_t)stream);
+}
+
+static int spectrogram_checked(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int pad_mode,
+                               float* d_spec, cudaStream_t stream) {
     if (!ctx) return SSB_E_INVALID_ARG;
     if (B == 0) return SSB_OK;
     if (B < 0 || B > 65535 || !d_wave || !d_spec || sr < SSB_N_FFT || wave_stride < sr ||
@@ -675,12 +830,54 @@ extern "C" int ssb_spectrogram_batch(ssb_ctx* ctx, int B, const float* d_wave, i
     return SSB_OK;
 }
 
+// convolve + spectrogram.  With ssb_set_streams(ctx, S > 1) the batch is split into S sub-batches whose
+// kernel chains run on S internal streams forked from / joined to the caller's stream: the tail of one
+// kernel (partial last wave) overlaps the next sub-batch's work, and memory-bound kernels of one chain
+// overlap compute-bound kernels of another.
 extern "C" int ssb_render_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs, const float* d_rir_bank,
                                 const void* d_xpool, void* d_hscratch, float* d_wave, int64_t wave_stride, int pad_mode,
                                 float* d_spec, void* stream) {
-    int rc = ssb_convolve_batch(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_hscratch, d_wave, wave_stride, stream);
+    int S = ctx ? ctx->n_streams : 1;
+    if (S > SSB_MAX_STREAMS) S = SSB_MAX_STREAMS;
+    if (S > B / 32) S = B / 32;                       // sub-batches of at least 32 envs
+    if (S <= 1) {
+        int rc = ssb_convolve_batch(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_hscratch, d_wave, wave_stride, stream);
+        if (rc) return rc;
+        return ssb_spectrogram_batch(ctx, B, d_wave, wave_stride, plan->sr, pad_mode, d_spec, stream);
+    }
+    int rc = check_plan(ctx, plan);
     if (rc) return rc;
-    return ssb_spectrogram_batch(ctx, B, d_wave, wave_stride, plan->sr, pad_mode, d_spec, stream);
+    if (B > 65535 || !d_reqs || !d_rir_bank || !d_xpool || !d_hscratch || !d_wave || !d_spec || wave_stride < plan->sr)
+        SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_render_batch: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ctx->s_comp[0]) {
+        for (int i = 0; i < SSB_MAX_STREAMS; ++i) {
+            SSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_comp[i], cudaStreamNonBlocking));
+            SSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+        }
+        SSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    }
+    SSB_CUDA(ctx, ensure_yscratch(ctx, plan, B, st));
+    SSB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    const size_t spec_row = (size_t)SSB_SPEC_ROWS * ssb_spec_cols(plan->sr) * 2;
+    const size_t y_env = (size_t)plan->n_blocks * ((size_t)1 << plan->log2n);
+    const int per = (B + S - 1) / S;
+    int i = 0;
+    for (int e0 = 0; e0 < B; e0 += per, ++i) {
+        const int nb = (B - e0 < per) ? (B - e0) : per;
+        cudaStream_t si = ctx->s_comp[i];
+        SSB_CUDA(ctx, cudaStreamWaitEvent(si, ctx->ev_fork, 0));
+        SSB_CUDA(ctx, launch_conv_any(ctx, plan, nb, d_reqs + e0, d_rir_bank, d_xpool,
+                                      (float2*)d_hscratch + (size_t)e0 * plan->h_elems_per_env,
+                                      ctx->yscratch ? ctx->yscratch + (size_t)e0 * y_env : nullptr,
+                                      d_wave + (size_t)e0 * 2 * wave_stride, wave_stride, si));
+        rc = spectrogram_checked(ctx, nb, d_wave + (size_t)e0 * 2 * wave_stride, wave_stride, plan->sr, pad_mode,
+                                 d_spec + (size_t)e0 * spec_row, si);
+        if (rc) return rc;
+        SSB_CUDA(ctx, cudaEventRecord(ctx->ev_comp[i], si));
+        SSB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_comp[i], 0));
+    }
+    return SSB_OK;
 }
 
 // Host-buffer entry.  n_chunks > 1 pipelines the batch: chunk c+1's H2D copy (copy stream) overlaps
@@ -717,12 +914,15 @@ extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, 
         SSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
         for (int i = 0; i < 2 * SSB_MAX_CHUNKS + 2; ++i)
             SSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) SSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_done[i], cudaEventDisableTiming));
     }
-    cudaEvent_t ev_entry = ctx->ev[2 * SSB_MAX_CHUNKS], ev_done = ctx->ev[2 * SSB_MAX_CHUNKS + 1];
-    // copies must not overtake earlier work on the caller's stream that still uses the staging buffers
-    SSB_CUDA(ctx, cudaEventRecord(ev_entry, st));
-    SSB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_entry, 0));
-    SSB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev_entry, 0));
+    cudaEvent_t ev_done = ctx->ev[2 * SSB_MAX_CHUNKS + 1];
+    // The H2D copies only have to wait for the kernels that last read THIS staging buffer.  A caller
+    // that alternates two staging buffers (HostSession does) therefore gets the next step's copy
+    // overlapped with the current step's kernels; with a single buffer the copy waits for them.
+    for (int i = 0; i < 2; ++i)
+        if (ctx->stage_ptr[i] == (const void*)d_rir_staging || ctx->stage_ptr[i] == (const void*)d_reqs_staging)
+            SSB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_h2d, ctx->stage_done[i], 0));
     SSB_CUDA(ctx, cudaMemcpyAsync(d_reqs_staging, h_reqs, (size_t)B * sizeof(ssb_req), cudaMemcpyHostToDevice, ctx->s_h2d));
     const int64_t bank_taps = rir_bytes / (int64_t)sizeof(float2);
     const int per = (B + n_chunks - 1) / n_chunks;
@@ -760,6 +960,12 @@ extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, 
                                             d_wave + (size_t)e0 * 2 * wave_stride, (size_t)wave_stride * sizeof(float),
                                             (size_t)plan->sr * sizeof(float), (size_t)nb * 2, cudaMemcpyDeviceToHost,
                                             ctx->s_d2h));
+    }
+    {   // remember who read this staging buffer last
+        const int slot = ctx->stage_next;
+        ctx->stage_next ^= 1;
+        ctx->stage_ptr[slot] = (const void*)d_rir_staging;
+        SSB_CUDA(ctx, cudaEventRecord(ctx->stage_done[slot], st));
     }
     // the caller's stream completes when the last D2H copy has landed
     SSB_CUDA(ctx, cudaEventRecord(ev_done, ctx->s_d2h));

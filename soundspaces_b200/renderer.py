@@ -94,6 +94,14 @@ class BatchedAudioRenderer:
         self._wave = None
         self._prev_wave = None
 
+    def set_conv_mode(self, mode: int):
+        """0 = per-bin partition sums then inverse FFTs (default); 1 = fused into the inverse-FFT kernel."""
+        self.ctx.check(self.lib.ssb_set_conv_mode(self.ctx.handle, int(mode)), "ssb_set_conv_mode")
+
+    def set_streams(self, n: int):
+        """Run render() as n sub-batches on n internal streams (overlaps kernel tails)."""
+        self.ctx.check(self.lib.ssb_set_streams(self.ctx.handle, int(n)), "ssb_set_streams")
+
     # ------------------------------------------------------------------ banks
     def add_rirs(self, rirs: Sequence) -> list:
         """Append RIRs ((L, 2) float32 arrays / tensors; None or empty => zero-RIR fallback)."""
@@ -322,8 +330,10 @@ class HostSession:
         self.h_spec = torch.empty((n,) + r.spec_shape, dtype=torch.float32).pin_memory()
         self.h_wave = torch.empty((n, 2, r.sr), dtype=torch.float32).pin_memory() if want_wave else None
         self.h_reqs = torch.empty(n * REQ_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-        self.d_rir = torch.empty((n, taps, 2), dtype=torch.float32, device=r.device)
-        self.d_reqs = torch.empty(n * REQ_DTYPE.itemsize, dtype=torch.uint8, device=r.device)
+        # two device staging sets, alternated per step: the copy of step k+1 overlaps the kernels of step k
+        self.d_rir = [torch.empty((n, taps, 2), dtype=torch.float32, device=r.device) for _ in range(2)]
+        self.d_reqs = [torch.empty(n * REQ_DTYPE.itemsize, dtype=torch.uint8, device=r.device) for _ in range(2)]
+        self._step = 0
         self.d_spec = torch.empty((n,) + r.spec_shape, dtype=torch.float32, device=r.device)
         self.h2d_bytes = self.h_rir.numel() * 4 + self.h_reqs.numel()
         self.d2h_bytes = self.h_spec.numel() * 4 + (self.h_wave.numel() * 4 if want_wave else 0)
@@ -347,12 +357,15 @@ class HostSession:
         self.h_reqs.numpy()[:] = reqs.view(np.uint8).reshape(-1)
 
     def run(self):
-        """Enqueue H2D + kernels + D2H on the current stream (asynchronous)."""
+        """Enqueue H2D + kernels + D2H (asynchronous; the current stream completes when the results
+        have landed in ``h_spec`` / ``h_wave``).  ``h_rir`` must not be refilled before that."""
         r = self.r
         hs, wave = r._scratch(self.n)
+        d_rir, d_reqs = self.d_rir[self._step & 1], self.d_reqs[self._step & 1]
+        self._step += 1
         r.ctx.check(r.lib.ssb_render_batch_host(
             r.ctx.handle, C.byref(r.plan), self.n, self.h_reqs.data_ptr(), self.h_rir.data_ptr(),
-            self.h_rir.numel() * 4, self.d_rir.data_ptr(), self.d_reqs.data_ptr(), r._xpool.data_ptr(),
+            self.h_rir.numel() * 4, d_rir.data_ptr(), d_reqs.data_ptr(), r._xpool.data_ptr(),
             hs.data_ptr(), wave.data_ptr(), r.sr, r.pad_mode, self.d_spec.data_ptr(), self.h_spec.data_ptr(),
             self.h_wave.data_ptr() if self.h_wave is not None else None, self.n_chunks, r._stream()),
             "ssb_render_batch_host")

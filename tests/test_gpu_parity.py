@@ -146,11 +146,14 @@ def test_singing_fixture(golden):
     check_spec(spec[0].cpu().numpy(), golden["singing/spec_reflect"])
 
 
-def test_ragged_batch_matches_oracle():
-    """Mixed batch: ragged RIR lengths, zero-RIR fallback, silent envs, different offsets."""
+@pytest.mark.parametrize("conv_mode", [0, 1])
+def test_ragged_batch_matches_oracle(conv_mode):
+    """Mixed batch: ragged RIR lengths, zero-RIR fallback, silent envs, different offsets; both
+    convolution schedules (per-bin partition sums / fused into the inverse FFT)."""
     from soundspaces_b200 import AudioRequest
     sr = 16000
     r = renderer(sr, 48000, n_terms=2)
+    r.set_conv_mode(conv_mode)
     clips = [make_source(40, sr), make_source(41, 5 * sr)]
     sids = [r.add_source(c) for c in clips]
     lens = [1, 17, 4095, 4096, 4097, 8192, 15999, 16000, 16001, 30011, 48000]
@@ -170,6 +173,7 @@ def test_ragged_batch_matches_oracle():
         check_spec(spec[i], ao.compute_spectrogram(ref.astype(np.float32)))
         if reqs[i].silent:
             assert not spec[i].any()
+    r.set_conv_mode(0)
 
 
 def test_full_size_c2_properties():
@@ -203,6 +207,13 @@ def test_full_size_c2_properties():
     torch.cuda.synchronize()
     assert np.array_equal(wave2.cpu().numpy(), wave_h[perm])
     assert np.array_equal(spec2.cpu().numpy(), spec_h[perm])
+    # sub-batches on internal streams: bit-identical to the single-stream result
+    for streams in (2, 3, 8):
+        r.set_streams(streams)
+        spec3, wave3 = r.render(reqs, want_wave=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(wave3.cpu().numpy(), wave_h) and np.array_equal(spec3.cpu().numpy(), spec_h)
+    r.set_streams(1)
 
 
 @pytest.mark.parametrize("n_chunks", [1, 3, 4, 32])
