@@ -23,6 +23,7 @@
  *                              soundspaces/simulator.py:690-701 for a batch of envs
  *   ssb_render_batch_host   <- the same with host buffers (what the per-env numpy API
  *                              of the reference hands over), copies included
+ *   ssb_sh_decode_batch     <- scripts/ambisonic_to_binaural.py:14-19 (closed AmbisonicBinauralizer ELF)
  *   ssb_pcm16_decode/encode <- int16 <-> float32 PCM (librosa.load decode used at
  *                              simulator.py:597; np.int16(audio*32767) at
  *                              scripts/interactive_demo.py:110)
@@ -162,6 +163,15 @@ int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_r
                           const float* h_rir, int64_t rir_bytes, float* d_rir_staging, ssb_req* d_reqs_staging,
                           const void* d_xpool, void* d_hscratch, float* d_wave, int64_t wave_stride,
                           int pad_mode, float* d_spec, float* h_spec, float* h_wave, int n_chunks, void* stream);
+
+/* Ambisonic -> binaural decode of a batch of 9-channel (ACN, second order) impulse responses:
+ * d_out_rir[env][n][ear] = sum_k sum_tau (R(az_env) a)_k[n - 128 - tau] * hbank[k][ear][tau], n < L,
+ * i.e. what scripts/ambisonic_to_binaural.py:14-19 obtains from the closed AmbisonicBinauralizer
+ * (rotation about the vertical axis, 9 x 2 FIR filters of 256 taps, 128-sample bulk delay, output
+ * cut to the input length).  d_amb: [B][L][9] f32; d_az_deg: [B] f32 degrees; d_hbank: [9][2][256] f32;
+ * d_filters: scratch of B * 9 * 256 float2; d_out_rir: [B][L][2] f32, directly usable as an RIR bank. */
+int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int L, const float* d_az_deg, const float* d_hbank,
+                        void* d_filters, float* d_out_rir, void* stream);
 
 /* PCM helpers.  decode: float32(x) / 32768 (exact).  encode mode 0: round(x*32768) saturated;
  * mode 1: trunc(x*32767) saturated (interactive_demo.py:110). */

@@ -464,6 +464,88 @@ spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr
 }
 
 // ---------------------------------------------------------------------------
+// ambisonic -> binaural decode (reference: scripts/ambisonic_to_binaural.py:14-19 driving the
+// closed AmbisonicBinauralizer): out[n][ear] = sum_k sum_tau (R(az) a)_k[n - 128 - tau] h[k][ear][tau].
+// The rotation is folded into per-env filters g[k][tau] = sum_j R[j][k] h[j][.][tau] (sh_filters_kernel),
+// then a direct-form FIR (9 channels x 256 taps, both ears as one float2) produces the (L, 2) RIR in the
+// interleaved layout the convolution kernels read.
+// ---------------------------------------------------------------------------
+constexpr int SH_CH = 9, SH_TAPS = 256, SH_DELAY = 128;
+constexpr int SH_THREADS = 128, SH_PER_THREAD = 8, SH_TILE = SH_THREADS * SH_PER_THREAD;   // outputs per CTA
+
+// grid (B); block 256: g[env][k][tau] (float2 = L,R)
+__global__ void __launch_bounds__(SH_TAPS)
+sh_filters_kernel(const float* __restrict__ hbank, const float* __restrict__ az_deg, float2* __restrict__ g) {
+    const int env = blockIdx.x, tau = threadIdx.x;
+    const float al = az_deg[env] * 0.017453292519943295f;
+    float c1, s1, c2, s2;
+    sincosf(al, &s1, &c1);
+    sincosf(2.f * al, &s2, &c2);
+    float2 h[SH_CH];
+#pragma unroll
+    for (int j = 0; j < SH_CH; ++j)
+        h[j] = make_float2(__ldg(hbank + (j * 2 + 0) * SH_TAPS + tau), __ldg(hbank + (j * 2 + 1) * SH_TAPS + tau));
+    // (R a)_j = sum_k R[j][k] a_k  =>  g_k = sum_j R[j][k] h_j; pairs (neg, pos, m): (1,3,1), (5,7,1), (4,8,2)
+    // R[pos][pos] = c, R[pos][neg] = -s, R[neg][pos] = s, R[neg][neg] = c
+    float2 o[SH_CH];
+    o[0] = h[0]; o[2] = h[2]; o[6] = h[6];
+    auto mix = [&](int neg, int pos, float c, float s) {
+        o[neg] = make_float2(c * h[neg].x - s * h[pos].x, c * h[neg].y - s * h[pos].y);     // column neg: R[neg][neg] h_neg + R[pos][neg] h_pos
+        o[pos] = make_float2(s * h[neg].x + c * h[pos].x, s * h[neg].y + c * h[pos].y);     // column pos: R[neg][pos] h_neg + R[pos][pos] h_pos
+    };
+    mix(1, 3, c1, s1);
+    mix(5, 7, c1, s1);
+    mix(4, 8, c2, s2);
+#pragma unroll
+    for (int k = 0; k < SH_CH; ++k) g[((long long)env * SH_CH + k) * SH_TAPS + tau] = o[k];
+}
+
+// grid (ceil(L / SH_TILE), B); block SH_THREADS.  amb[env][L][9] f32 -> out[env][L][2]
+__global__ void __launch_bounds__(SH_THREADS)
+sh_decode_kernel(const float* __restrict__ amb, int L, const float2* __restrict__ g, float* __restrict__ out) {
+    extern __shared__ float sh_smem[];
+    constexpr int SPAN = SH_TILE + SH_DELAY + SH_TAPS - 1;      // input samples feeding one tile
+    float* sa = sh_smem;                                          // [9][SPAN]
+    float2* sg = reinterpret_cast<float2*>(sh_smem + SH_CH * SPAN + (SH_CH * SPAN & 1));   // [9][256]
+    const int env = blockIdx.y;
+    const int n0 = blockIdx.x * SH_TILE;
+    const int first = n0 - SH_DELAY - (SH_TAPS - 1);              // input index of sa[.][0]
+    const float* __restrict__ a = amb + (long long)env * L * SH_CH;
+    for (int i = threadIdx.x; i < SPAN * SH_CH; i += SH_THREADS) {
+        const int pos = i / SH_CH, k = i - pos * SH_CH;            // coalesced over the interleaved (L, 9) input
+        const int n = first + pos;
+        sa[k * SPAN + pos] = (n >= 0 && n < L) ? __ldg(a + (long long)n * SH_CH + k) : 0.f;
+    }
+    for (int i = threadIdx.x; i < SH_CH * SH_TAPS; i += SH_THREADS) sg[i] = __ldg(g + (long long)env * SH_CH * SH_TAPS + i);
+    __syncthreads();
+    float2 acc[SH_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < SH_PER_THREAD; ++j) acc[j] = make_float2(0.f, 0.f);
+    // thread t owns outputs n0 + t + j*SH_THREADS (j < 8): out[n] = sum_k sum_tau a_k[n - 128 - tau] g_k[tau];
+    // in tile coordinates a_k[n - 128 - tau] = sa[k][(n - n0) + 255 - tau]
+    for (int k = 0; k < SH_CH; ++k) {
+        const float* __restrict__ ak = sa + k * SPAN + threadIdx.x + (SH_TAPS - 1);
+        const float2* __restrict__ gk = sg + k * SH_TAPS;
+#pragma unroll 4
+        for (int tau = 0; tau < SH_TAPS; ++tau) {
+            const float2 w = gk[tau];                             // broadcast
+#pragma unroll
+            for (int j = 0; j < SH_PER_THREAD; ++j) {
+                const float x = ak[j * SH_THREADS - tau];         // conflict-free: consecutive lanes
+                acc[j].x = fmaf(x, w.x, acc[j].x);
+                acc[j].y = fmaf(x, w.y, acc[j].y);
+            }
+        }
+    }
+    float2* __restrict__ o = reinterpret_cast<float2*>(out) + (long long)env * L;
+#pragma unroll
+    for (int j = 0; j < SH_PER_THREAD; ++j) {
+        const int n = n0 + threadIdx.x + j * SH_THREADS;
+        if (n < L) o[n] = acc[j];
+    }
+}
+
+// ---------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------
 __global__ void crossfade_kernel(const float* __restrict__ prev, float* __restrict__ cur, int n_fade,
@@ -970,6 +1052,30 @@ extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, 
     // the caller's stream completes when the last D2H copy has landed
     SSB_CUDA(ctx, cudaEventRecord(ev_done, ctx->s_d2h));
     SSB_CUDA(ctx, cudaStreamWaitEvent(st, ev_done, 0));
+    return SSB_OK;
+}
+
+extern "C" int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int L, const float* d_az_deg, const float* d_hbank,
+                                   void* d_filters, float* d_out_rir, void* stream) {
+    if (!ctx) return SSB_E_INVALID_ARG;
+    if (B == 0) return SSB_OK;
+    if (B < 0 || B > 65535 || L <= 0 || !d_amb || !d_az_deg || !d_hbank || !d_filters || !d_out_rir ||
+        ((uintptr_t)d_out_rir & 7) || ((uintptr_t)d_filters & 7))
+        SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_sh_decode_batch: bad arguments (B=%d L=%d)", B, L);
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int SPAN = SH_TILE + SH_DELAY + SH_TAPS - 1;
+    const size_t smem = (size_t)(SH_CH * SPAN + 1) * sizeof(float) + (size_t)SH_CH * SH_TAPS * sizeof(float2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SSB_CUDA(ctx, cudaFuncSetAttribute(sh_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    sh_filters_kernel<<<B, SH_TAPS, 0, st>>>(d_hbank, d_az_deg, (float2*)d_filters);
+    SSB_CUDA(ctx, cudaGetLastError());
+    dim3 g((L + SH_TILE - 1) / SH_TILE, B);
+    sh_decode_kernel<<<g, SH_THREADS, smem, st>>>(d_amb, L, (const float2*)d_filters, d_out_rir);
+    ctx->launches += 2;
+    SSB_CUDA(ctx, cudaGetLastError());
     return SSB_OK;
 }
 

@@ -93,6 +93,7 @@ class BatchedAudioRenderer:
         self._hscratch = None
         self._wave = None
         self._prev_wave = None
+        self._hbank = None
 
     def set_conv_mode(self, mode: int):
         """0 = per-bin partition sums then inverse FFTs (default); 1 = fused into the inverse-FFT kernel."""
@@ -178,6 +179,33 @@ class BatchedAudioRenderer:
         self.ctx.check(self.lib.ssb_pcm16_encode(self.ctx.handle, w.data_ptr(), w.numel(),
                                                  {"round": 0, "demo": 1}[mode], out.data_ptr(), self._stream()),
                        "ssb_pcm16_encode")
+        return out
+
+    # ------------------------------------------------------------ SH decode
+    def sh_decode(self, amb: torch.Tensor, azimuth_deg, hbank=None) -> torch.Tensor:
+        """Ambisonic (n, L, 9) -> binaural (n, L, 2) RIRs on the device: SH rotation about the
+        vertical axis + the 9 x 2 x 256-tap HRTF bank (scripts/ambisonic_to_binaural.py:14-19).
+        The result can be handed to :meth:`set_dense_rir_bank` / :meth:`add_rirs`."""
+        if self._hbank is None or hbank is not None:
+            if hbank is None:
+                import os
+                hbank = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "sh_hrtf_bank.npy"))
+            hb = torch.as_tensor(np.ascontiguousarray(hbank, dtype=np.float32))
+            if tuple(hb.shape) != (9, 2, 256):
+                raise ValueError("HRTF bank must be (9, 2, 256)")
+            self._hbank = hb.to(self.device)
+        amb = torch.as_tensor(amb, dtype=torch.float32).to(self.device).contiguous()
+        if amb.ndim != 3 or amb.shape[2] != 9:
+            raise ValueError(f"ambisonic RIRs must be (n, L, 9), got {tuple(amb.shape)}")
+        n, L, _ = amb.shape
+        az = torch.as_tensor(azimuth_deg, dtype=torch.float32).reshape(-1).to(self.device)
+        if az.numel() != n:
+            raise ValueError("one azimuth per RIR")
+        filt = torch.empty((n, 9, 256, 2), dtype=torch.float32, device=self.device)
+        out = torch.empty((n, L, 2), dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.ssb_sh_decode_batch(self.ctx.handle, n, amb.data_ptr(), L, az.data_ptr(),
+                                                    self._hbank.data_ptr(), filt.data_ptr(), out.data_ptr(),
+                                                    self._stream()), "ssb_sh_decode_batch")
         return out
 
     # ---------------------------------------------------------------- helpers
