@@ -24,6 +24,7 @@
  *   ssb_render_batch_host   <- the same with host buffers (what the per-env numpy API
  *                              of the reference hands over), copies included
  *   ssb_sh_decode_batch     <- scripts/ambisonic_to_binaural.py:14-19 (closed AmbisonicBinauralizer ELF)
+ *   ssb_intensity_batch     <- Intensity.get_observation, ss_baselines/av_wan/avwan_sensors.py:91-100
  *   ssb_pcm16_decode/encode <- int16 <-> float32 PCM (librosa.load decode used at
  *                              simulator.py:597; np.int16(audio*32767) at
  *                              scripts/interactive_demo.py:110)
@@ -172,6 +173,12 @@ int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_r
  * d_filters: scratch of B * 9 * 256 float2; d_out_rir: [B][L][2] f32, directly usable as an RIR bank. */
 int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int L, const float* d_az_deg, const float* d_hbank,
                         void* d_filters, float* d_out_rir, void* stream);
+
+/* AV-WaN Intensity sensor (ss_baselines/av_wan/avwan_sensors.py:91-100) for a batch of (2, sr)
+ * waveforms: d_out[env] = mean(x[:, i:i+num_frame]**2), i = first sample (min over ears) above 10 % of
+ * the clip maximum. */
+int ssb_intensity_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int num_frame,
+                        float* d_out, void* stream);
 
 /* PCM helpers.  decode: float32(x) / 32768 (exact).  encode mode 0: round(x*32768) saturated;
  * mode 1: trunc(x*32767) saturated (interactive_demo.py:110). */

@@ -204,6 +204,30 @@ def continuous_next_sample_index(sample_index, sr, step_time, source_len):
 
 
 # --------------------------------------------------------------------------
+# side consumers of the waveform
+# --------------------------------------------------------------------------
+def intensity(audiogoal, num_frame=150):
+    """``Intensity.get_observation`` (ss_baselines/av_wan/avwan_sensors.py:91-100)."""
+    nonzero_idx = np.min((audiogoal > 0.1 * audiogoal.max()).argmax(axis=1))
+    impulse = audiogoal[:, nonzero_idx: nonzero_idx + num_frame]
+    return np.mean(impulse ** 2)
+
+
+def savi_dataset_audiogoal(source, rir, sr, index):
+    """``AudioGoalDataset.compute_audiogoal`` (ss_baselines/savi/pretraining/audiogoal_dataset.py:114-140)
+    for a given ``index`` (the reference draws it with random.randint).  Its steady-state slice starts
+    one sample earlier than the simulator's (``[index*sr - L :]`` + 'valid' + drop last)."""
+    rir = fallback_rir(rir, sr)
+    if index * sr - rir.shape[0] < 0:
+        seg = source[: (index + 1) * sr]
+        conv = np.array([fftconvolve(seg, rir[:, ch]) for ch in range(rir.shape[-1])])
+        return conv[:, index * sr: (index + 1) * sr]
+    seg = source[index * sr - rir.shape[0]: (index + 1) * sr]
+    conv = np.array([fftconvolve(seg, rir[:, ch], mode="valid") for ch in range(rir.shape[-1])])
+    return conv[:, :-1]
+
+
+# --------------------------------------------------------------------------
 # PCM helpers (A1: librosa.load -> soundfile decode; interactive_demo.py:110)
 # --------------------------------------------------------------------------
 def pcm16_to_float32(x):

@@ -561,6 +561,49 @@ __global__ void crossfade_kernel(const float* __restrict__ prev, float* __restri
     cur[o] = prev[o] * w1 + cur[o] * w2;
 }
 
+// Intensity sensor of AV-WaN (ss_baselines/av_wan/avwan_sensors.py:91-100): onset = the first sample (min
+// over ears) exceeding 10 % of the clip maximum; result = mean square of the num_frame samples after it.
+// grid (B); block 256
+__global__ void __launch_bounds__(256)
+intensity_kernel(const float* __restrict__ wave, long long wave_stride, int sr, int num_frame, float* __restrict__ out) {
+    __shared__ float sf[256];
+    __shared__ int si[256];
+    const int env = blockIdx.x, t = threadIdx.x;
+    const float* __restrict__ yl = wave + (long long)env * 2 * wave_stride;
+    const float* __restrict__ yr = yl + wave_stride;
+    float m = -INFINITY;
+    for (int n = t; n < sr; n += 256) m = fmaxf(m, fmaxf(yl[n], yr[n]));
+    sf[t] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (t < s) sf[t] = fmaxf(sf[t], sf[t + s]); __syncthreads(); }
+    const float thr = 0.1f * sf[0];
+    __syncthreads();
+    // first index per ear with value > thr (np.argmax of an all-False row is 0), then min over ears
+    int fl = sr, fr = sr;
+    for (int n = t; n < sr; n += 256) {
+        if (yl[n] > thr && n < fl) fl = n;
+        if (yr[n] > thr && n < fr) fr = n;
+    }
+    si[t] = fl;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (t < s) si[t] = min(si[t], si[t + s]); __syncthreads(); }
+    const int first_l = si[0] == sr ? 0 : si[0];
+    __syncthreads();
+    si[t] = fr;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (t < s) si[t] = min(si[t], si[t + s]); __syncthreads(); }
+    const int first_r = si[0] == sr ? 0 : si[0];
+    const int idx = min(first_l, first_r);
+    const int end = min(idx + num_frame, sr);               // numpy slicing clips at the end of the clip
+    float acc = 0.f;
+    for (int n = idx + t; n < end; n += 256) acc += yl[n] * yl[n] + yr[n] * yr[n];
+    __syncthreads();
+    sf[t] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (t < s) sf[t] += sf[t + s]; __syncthreads(); }
+    if (t == 0) out[env] = end > idx ? sf[0] / (float)(2 * (end - idx)) : nanf("");
+}
+
 __global__ void pcm16_decode_kernel(const int16_t* __restrict__ in, long long n, float* __restrict__ out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x;
@@ -1075,6 +1118,18 @@ extern "C" int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int 
     dim3 g((L + SH_TILE - 1) / SH_TILE, B);
     sh_decode_kernel<<<g, SH_THREADS, smem, st>>>(d_amb, L, (const float2*)d_filters, d_out_rir);
     ctx->launches += 2;
+    SSB_CUDA(ctx, cudaGetLastError());
+    return SSB_OK;
+}
+
+extern "C" int ssb_intensity_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int num_frame,
+                                   float* d_out, void* stream) {
+    if (!ctx) return SSB_E_INVALID_ARG;
+    if (B == 0) return SSB_OK;
+    if (B < 0 || !d_wave || !d_out || sr <= 0 || wave_stride < sr || num_frame <= 0)
+        SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_intensity_batch: bad arguments");
+    intensity_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(d_wave, (long long)wave_stride, sr, num_frame, d_out);
+    ctx->launches += 1;
     SSB_CUDA(ctx, cudaGetLastError());
     return SSB_OK;
 }

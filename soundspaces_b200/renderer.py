@@ -181,6 +181,17 @@ class BatchedAudioRenderer:
                        "ssb_pcm16_encode")
         return out
 
+    def intensity(self, wave: torch.Tensor, num_frame: int = 150) -> torch.Tensor:
+        """AV-WaN ``Intensity`` (avwan_sensors.py:91-100) for a (n, 2, sr) CUDA batch -> (n,) mean squares."""
+        if wave.ndim == 2:
+            wave = wave[None]
+        wave = wave.to(self.device, torch.float32).contiguous()
+        out = torch.empty(wave.shape[0], dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.ssb_intensity_batch(self.ctx.handle, wave.shape[0], wave.data_ptr(), wave.shape[2],
+                                                    wave.shape[2], int(num_frame), out.data_ptr(), self._stream()),
+                       "ssb_intensity_batch")
+        return out
+
     # ------------------------------------------------------------ SH decode
     def sh_decode(self, amb: torch.Tensor, azimuth_deg, hbank=None) -> torch.Tensor:
         """Ambisonic (n, L, 9) -> binaural (n, L, 2) RIRs on the device: SH rotation about the

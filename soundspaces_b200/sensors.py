@@ -131,6 +131,33 @@ class SpectrogramSensor(Sensor):
 setattr(SpectrogramSensor.compute_spectrogram, SPECTROGRAM_NATIVE_ATTR, True)
 
 
+@registry.register_sensor(name="Intensity")
+class Intensity(Sensor):
+    """AV-WaN ``Intensity`` sensor (ss_baselines/av_wan/avwan_sensors.py:69-100): mean square of the 150
+    samples after the onset of the current waveform, reduced on the device."""
+
+    def __init__(self, sim, config, *args: Any, **kwargs: Any):
+        self._sim = sim
+        super().__init__(config=config)
+
+    def _get_uuid(self, *args: Any, **kwargs: Any):
+        return "intensity"
+
+    def _get_sensor_type(self, *args: Any, **kwargs: Any):
+        return getattr(SensorTypes, "COLOR", "COLOR")
+
+    def _get_observation_space(self, *args: Any, **kwargs: Any):
+        return spaces.Box(low=0, high=1, shape=(1,), dtype=bool)
+
+    def get_observation(self, *args: Any, observations=None, episode=None, **kwargs: Any):
+        from .simulator import AudioRenderService
+        audiogoal = np.asarray(self._sim.get_current_audiogoal_observation())
+        r = AudioRenderService.get(audiogoal.shape[1], getattr(self._sim, "b200_device", "cuda:0"),
+                                   pad_mode=getattr(self._sim, "b200_pad_mode", "reflect")).renderer
+        rms = r.intensity(torch.from_numpy(np.ascontiguousarray(audiogoal, dtype=np.float32))[None])
+        return [float(rms[0])]
+
+
 def to_tensor(v):
     # ss_baselines/common/utils.py:117-123
     if torch.is_tensor(v):

@@ -250,3 +250,49 @@ def test_error_reporting():
     rc = r.lib.ssb_spectrogram_batch(r.ctx.handle, 1, None, 100, 100, 0, None, None)
     assert rc == -1 and b"ssb_spectrogram_batch" in r.lib.ssb_last_error(r.ctx.handle)
     assert _lib.load_library().ssb_version() >= 100
+
+
+def test_intensity_sensor_kernel():
+    """N3: AV-WaN Intensity (avwan_sensors.py:91-100) on the device vs the oracle."""
+    sr = 16000
+    r = renderer(sr, 6000)
+    rng = np.random.default_rng(4)
+    waves = []
+    for i in range(6):
+        w = (rng.standard_normal((2, sr)) * np.exp(-np.arange(sr) / 3000.0)).astype(np.float32)
+        w[:, : 500 * i] *= 1e-3                       # onset later and later
+        waves.append(w)
+    waves.append(np.zeros((2, sr), np.float32))       # silent: onset 0, mean square 0
+    late = np.zeros((2, sr), np.float32); late[0, sr - 20] = 1.0     # window clipped at the end of the clip
+    waves.append(late)
+    neg = -np.abs(waves[0])                           # max <= 0: every sample of the max ear passes, onset per argmax rule
+    waves.append(neg.astype(np.float32))
+    w = np.stack(waves)
+    got = r.intensity(torch.from_numpy(w).cuda()).cpu().numpy()
+    for i in range(len(w)):
+        ref = ao.intensity(w[i])
+        assert np.isclose(got[i], ref, rtol=1e-5, atol=1e-12), (i, got[i], ref)
+
+
+def test_savi_pretraining_dataset_quirk():
+    """N4: the dataset's steady-state slice starts one sample earlier than the simulator's."""
+    from soundspaces_b200.pretraining import BatchedAudioGoalDataset
+    sr = 16000
+    r = renderer(sr, 48000, n_terms=2)
+    clips = [make_source(60, 5 * sr), make_source(61, 3 * sr)]
+    sids = [r.add_source(c) for c in clips]
+    rirs = [make_rir(70, 7001), make_rir(71, 20000), None]
+    rids = r.add_rirs(rirs)
+    files = [(rids[a], sids[b]) for a in range(3) for b in range(2)]
+    ds = BatchedAudioGoalDataset(r, files)
+    items, indices = [], []
+    for item, (rid, sid) in enumerate(files):
+        for index in range(ds.audio_length(sid) - 1):
+            items.append(item); indices.append(index)
+    spec, wave = ds.render(items, indices, want_wave=True)
+    torch.cuda.synchronize()
+    for k, (item, index) in enumerate(zip(items, indices)):
+        a, b = divmod(item, 2)
+        ref = ao.savi_dataset_audiogoal(clips[b], rirs[a], sr, index)
+        check_wave(wave[k].cpu().numpy(), ref)
+        check_spec(spec[k].cpu().numpy(), ao.compute_spectrogram(ref.astype(np.float32)))
