@@ -235,11 +235,11 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __re
     }
     // leftover radix-M across M adjacent lanes (DIF)
     if constexpr (P::M == 2) {
-        const bool up = t & 1;
+        const float sgn = (t & 1) ? -1.f : 1.f;                // lower lane: v + o, upper lane: o - v  (one FFMA each)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             float2 o = make_float2(__shfl_xor_sync(0xffffffffu, v[i].x, 1), __shfl_xor_sync(0xffffffffu, v[i].y, 1));
-            v[i] = up ? csub(o, v[i]) : cadd(v[i], o);
+            v[i] = make_float2(fmaf(sgn, v[i].x, o.x), fmaf(sgn, v[i].y, o.y));
         }
     } else if constexpr (P::M == 4) {
         const int j = t & 3;
@@ -263,11 +263,11 @@ __device__ __forceinline__ void fft_inverse(float2 (&v)[16], int t, float2* __re
                                             const float2* __restrict__ gtw0, const float2* __restrict__ stw) {
     using P = FftPlan<LOG2N>;
     if constexpr (P::M == 2) {
-        const bool up = t & 1;
+        const float sgn = (t & 1) ? -1.f : 1.f;                // lower lane: v + o, upper lane: o - v  (one FFMA each)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             float2 o = make_float2(__shfl_xor_sync(0xffffffffu, v[i].x, 1), __shfl_xor_sync(0xffffffffu, v[i].y, 1));
-            v[i] = up ? csub(o, v[i]) : cadd(v[i], o);
+            v[i] = make_float2(fmaf(sgn, v[i].x, o.x), fmaf(sgn, v[i].y, o.y));
         }
     } else if constexpr (P::M == 4) {
         const int j = t & 3;

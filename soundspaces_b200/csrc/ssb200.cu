@@ -443,8 +443,12 @@ spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr
         spec_column<REFLECT, true>(yl, yr, sr, n_frames, col, lane, xbuf, tw, window, accl, accr, acc64l, acc64r, dbg);
     else
         spec_column<REFLECT, false>(yl, yr, sr, n_frames, col, lane, xbuf, tw, window, accl, accr, acc64l, acc64r, dbg);
-    // pool 4 adjacent bins (lanes), scale: 0.5 (packing) / 16 (4x4 mean), log1p, store
+    // pool 4 adjacent bins (lanes): after the two xor-shuffles every lane of a 4-lane group holds the group sum;
+    // lane q of the group then finishes rows m = 2q, 2q+1 only (4 log1p per lane instead of 16).
+    // scale: 0.5 (ear packing) / 16 (4x4 mean)
     float* __restrict__ o = out + (((long long)env * SSB_SPEC_ROWS) * cols + col) * 2;
+    const int q = lane & 3;
+    float ml[2] = {0.f, 0.f}, mr[2] = {0.f, 0.f};
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
         float l = accl[m], r = accr[m];
@@ -452,11 +456,13 @@ spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr
         r += __shfl_xor_sync(0xffffffffu, r, 1);
         l += __shfl_xor_sync(0xffffffffu, l, 2);
         r += __shfl_xor_sync(0xffffffffu, r, 2);
-        if ((lane & 3) == 0) {
-            const int row = (lane >> 2) + 8 * m;
-            *reinterpret_cast<float2*>(o + (long long)row * cols * 2) =
-                make_float2(log1pf(l * (0.5f / 16.0f)), log1pf(r * (0.5f / 16.0f)));
-        }
+        if (q == (m >> 1)) { ml[m & 1] = l; mr[m & 1] = r; }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int row = (lane >> 2) + 8 * (2 * q + j);
+        *reinterpret_cast<float2*>(o + (long long)row * cols * 2) =
+            make_float2(log1pf(ml[j] * (0.5f / 16.0f)), log1pf(mr[j] * (0.5f / 16.0f)));
     }
     if (lane == 0)
         *reinterpret_cast<float2*>(o + (long long)64 * cols * 2) =
