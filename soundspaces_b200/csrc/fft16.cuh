@@ -35,20 +35,64 @@
 
 namespace ssb {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// ---------------------------------------------------------------------------------------------
+// Complex arithmetic on PACKED FP32 pairs.  sm_100a has two-wide FP32 instructions (FADD2 / FMUL2 /
+// FFMA2 on 64-bit register pairs, PTX add/mul/fma.f32x2) with per-operand swap (LO_HI), scalar
+// broadcast (.F32) and per-half negate modifiers.  A float2 complex number is exactly such a pair, so a
+// complex add is ONE instruction, a complex multiply TWO, and multiplying by +-i is free (folded into
+// the consumer's operand modifiers by ptxas).  The FP32 pipe does the same flops per clock either way
+// (measured on B200: 36.6 vs 35.0 TFLOP/s), but these kernels are issue-bound (issue slots 60-77 %
+// busy, FMA pipe 37-49 %), and the packed forms need half the issue slots.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; "
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+__device__ __forceinline__ float2 bcast(float x) { return make_float2(x, x); }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return sub2(a, b); }
+// a * b = a.x * (b.x, b.y) + a.y * (-b.y, b.x)          (FMUL2 + FFMA2)
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    const float2 t = mul2(bcast(a.y), make_float2(b.y, b.x));
+    return fma2(bcast(a.x), b, make_float2(-t.x, t.y));
 }
-// a * conj(b)
+// a * conj(b) = a.x * (b.x, -b.y) + a.y * (b.y, b.x)
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
-    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+    const float2 t = mul2(bcast(a.y), make_float2(b.y, b.x));
+    return fma2(bcast(a.x), make_float2(b.x, -b.y), t);
 }
-// a * (-i) and a * (+i)
+// acc + a * b   (FFMA2 + FMUL2 + FADD2: the half-negation folds into the add's operand modifier)
+__device__ __forceinline__ float2 cfma(float2 a, float2 b, float2 acc) {
+    const float2 t = mul2(bcast(a.y), make_float2(b.y, b.x));
+    return add2(fma2(bcast(a.x), b, acc), make_float2(-t.x, t.y));
+}
+// a * (-i) and a * (+i): pure operand swizzles
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
 __device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }
 
-// 4-point DFT, in place.  Forward: w4 = -i.  Inverse: w4 = +i.
+// 4-point DFT, in place.  Forward: w4 = -i.  Inverse: w4 = +i.   (8 FADD2)
 template <bool INV>
 __device__ __forceinline__ void bfly4(float2& a0, float2& a1, float2& a2, float2& a3) {
     float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
@@ -60,29 +104,22 @@ __device__ __forceinline__ void bfly4(float2& a0, float2& a1, float2& a2, float2
 }
 
 // multiply by w16^k (forward) or conj(w16^k) (inverse), k a compile-time constant
-template <bool INV>
-__device__ __forceinline__ float2 mul_cs(float2 a, float c, float s) {
-    // forward multiplies by (c - i s), inverse by (c + i s)
-    const float ss = INV ? -s : s;
-    return make_float2(a.x * c + a.y * ss, a.y * c - a.x * ss);
-}
 template <bool INV, int K>
 __device__ __forceinline__ float2 mul_w16(float2 a) {
     constexpr float C1 = 0.92387953251128674f;   // cos(pi/8)
     constexpr float S1 = 0.38268343236508977f;   // sin(pi/8)
     constexpr float R2 = 0.70710678118654752f;
     static_assert(K == 0 || K == 1 || K == 2 || K == 3 || K == 4 || K == 6 || K == 9, "unsupported w16 power");
+    // forward twiddle w16^k = cos(k pi/8) - i sin(k pi/8); the inverse uses the conjugate
     if constexpr (K == 0) return a;
-    else if constexpr (K == 1) return mul_cs<INV>(a, C1, S1);
-    else if constexpr (K == 2)                   // (x+iy)(1 -+ i) R2
-        return INV ? make_float2((a.x - a.y) * R2, (a.x + a.y) * R2)
-                   : make_float2((a.x + a.y) * R2, (a.y - a.x) * R2);
-    else if constexpr (K == 3) return mul_cs<INV>(a, S1, C1);
+    else if constexpr (K == 1) return cmul(a, make_float2(C1, INV ? S1 : -S1));
+    else if constexpr (K == 2)                   // R2 (1 -+ i) a = R2 (a + (-+i) a)
+        return mul2(cadd(a, INV ? mul_pi(a) : mul_mi(a)), bcast(R2));
+    else if constexpr (K == 3) return cmul(a, make_float2(S1, INV ? C1 : -C1));
     else if constexpr (K == 4) return INV ? mul_pi(a) : mul_mi(a);
-    else if constexpr (K == 6)                   // w16^6 = -R2 - i R2 (forward), conj = -R2 + i R2
-        return INV ? make_float2((-a.x - a.y) * R2, (a.x - a.y) * R2)
-                   : make_float2((a.y - a.x) * R2, (-a.x - a.y) * R2);
-    else return mul_cs<INV>(a, -C1, -S1);        // K == 9
+    else if constexpr (K == 6)                   // R2 (-1 -+ i) a = R2 ((-+i) a - a)
+        return mul2(csub(INV ? mul_pi(a) : mul_mi(a), a), bcast(R2));
+    else return cmul(a, make_float2(-C1, INV ? -S1 : S1));   // K == 9
 }
 
 // the six inter-pass twiddles of one thread for one pass: r[k-1] = w^(j k), m[k-1] = w^(4 j k), k = 1..3
@@ -239,7 +276,7 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __re
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             float2 o = make_float2(__shfl_xor_sync(0xffffffffu, v[i].x, 1), __shfl_xor_sync(0xffffffffu, v[i].y, 1));
-            v[i] = make_float2(fmaf(sgn, v[i].x, o.x), fmaf(sgn, v[i].y, o.y));
+            v[i] = fma2(bcast(sgn), v[i], o);
         }
     } else if constexpr (P::M == 4) {
         const int j = t & 3;
@@ -267,7 +304,7 @@ __device__ __forceinline__ void fft_inverse(float2 (&v)[16], int t, float2* __re
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             float2 o = make_float2(__shfl_xor_sync(0xffffffffu, v[i].x, 1), __shfl_xor_sync(0xffffffffu, v[i].y, 1));
-            v[i] = make_float2(fmaf(sgn, v[i].x, o.x), fmaf(sgn, v[i].y, o.y));
+            v[i] = fma2(bcast(sgn), v[i], o);
         }
     } else if constexpr (P::M == 4) {
         const int j = t & 3;

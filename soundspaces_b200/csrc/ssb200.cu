@@ -203,15 +203,18 @@ mac_bins_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
 #pragma unroll
             for (int b = 0; b < NBMAX; ++b) {
                 if (b < nblk) {
-                    float2 acc = first ? make_float2(0.f, 0.f) : yo[(long long)b * P::N];
+                    // x * h = x.x * h + i * (x.y * h): two accumulators, ONE swizzled add at the end, so the
+                    // inner loop is two FFMA2 per complex multiply-accumulate with no operand shuffling
+                    float2 acc_re = first ? make_float2(0.f, 0.f) : yo[(long long)b * P::N];
+                    float2 acc_im = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int p = 0; p < NPMAX; ++p) {
-                        if (p <= b) {                           // window b - p >= 0; h[p] is 0 beyond nparts
-                            acc.x = fmaf(x[b - p].x, h[p].x, fmaf(-x[b - p].y, h[p].y, acc.x));
-                            acc.y = fmaf(x[b - p].x, h[p].y, fmaf(x[b - p].y, h[p].x, acc.y));
+                        if (p <= b) {                            // window b - p >= 0; h[p] is 0 beyond nparts
+                            acc_re = fma2(bcast(x[b - p].x), h[p], acc_re);
+                            acc_im = fma2(bcast(x[b - p].y), h[p], acc_im);
                         }
                     }
-                    yo[(long long)b * P::N] = acc;
+                    yo[(long long)b * P::N] = add2(acc_re, make_float2(-acc_im.y, acc_im.x));
                 }
             }
         } else {
@@ -223,8 +226,7 @@ mac_bins_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
                 for (int p = p_lo; p <= p_hi; ++p) {
                     const float2 h = hp[(long long)p * P::N];
                     const float2 x = __ldg(xp + (long long)(b - p + ct.x_wofs) * P::N);
-                    acc.x = fmaf(x.x, h.x, fmaf(-x.y, h.y, acc.x));
-                    acc.y = fmaf(x.x, h.y, fmaf(x.y, h.x, acc.y));
+                    acc = cfma(x, h, acc);
                 }
                 yo[(long long)b * P::N] = acc;
             }
@@ -296,10 +298,7 @@ mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
 #pragma unroll
             for (int i = 0; i < 16; ++i) { h[i] = hp[i * P::T]; x[i] = __ldg(xp + i * P::T); }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                acc[i].x = fmaf(x[i].x, h[i].x, fmaf(-x[i].y, h[i].y, acc[i].x));
-                acc[i].y = fmaf(x[i].x, h[i].y, fmaf(x[i].y, h[i].x, acc[i].y));
-            }
+            for (int i = 0; i < 16; ++i) acc[i] = cfma(x[i], h[i], acc[i]);
         }
     }
     }
@@ -358,22 +357,22 @@ __device__ __forceinline__ void spec_column(const float* __restrict__ yl, const 
                                             float (&accl)[8], float (&accr)[8], float& acc64l, float& acc64r, int dbg) {
     const Tw6 w0 = load_tw6<true>(stw, 32, lane);
     const int n0 = col * SSB_POOL * SSB_HOP - SSB_N_FFT / 2 + lane;          // sample of x_0 for this lane
-    float xl[15], xr[15];                                                    // window of the current frame: x[q], q = 1..14
+    float2 x[15];                                                            // window of the current frame: (L, R) pairs, q = 1..14
 #pragma unroll
-    for (int q = 1; q < 15; ++q) {
-        xl[q] = (dbg & 4) ? 0.f : spec_sample<REFLECT, INTERIOR>(yl, n0 + 32 * q, sr);
-        xr[q] = (dbg & 4) ? 0.f : spec_sample<REFLECT, INTERIOR>(yr, n0 + 32 * q, sr);
-    }
+    for (int q = 1; q < 15; ++q)
+        x[q] = (dbg & 4) ? make_float2(0.f, 0.f)
+                         : make_float2(spec_sample<REFLECT, INTERIOR>(yl, n0 + 32 * q, sr),
+                                       spec_sample<REFLECT, INTERIOR>(yr, n0 + 32 * q, sr));
 #pragma unroll 1
     for (int fr = 0; fr < SSB_POOL; ++fr) {
         // prefetch the 5 new samples of the next frame (j = 15 + 5 fr ..); latency hides behind this frame's FFT
-        float nl[5], nr[5];
+        float2 nx[5];
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
             const int n = n0 + 32 * (15 + 5 * fr + u);
             const bool need = fr + 1 < SSB_POOL && !(dbg & 4);
-            nl[u] = need ? spec_sample<REFLECT, INTERIOR>(yl, n, sr) : 0.f;
-            nr[u] = need ? spec_sample<REFLECT, INTERIOR>(yr, n, sr) : 0.f;
+            nx[u] = need ? make_float2(spec_sample<REFLECT, INTERIOR>(yl, n, sr), spec_sample<REFLECT, INTERIOR>(yr, n, sr))
+                         : make_float2(0.f, 0.f);
         }
         const bool f_ok = INTERIOR || (col * SSB_POOL + fr < n_frames);     // frames past the end add 0 (block_reduce pads with 0)
         float2 v[16];
@@ -382,7 +381,7 @@ __device__ __forceinline__ void spec_column(const float* __restrict__ yl, const 
 #pragma unroll
         for (int q = 1; q < 15; ++q) {
             const float w = f_ok ? __ldg(swin + lane + 32 * q) : 0.f;  // centre-padded Hann: 0 for idx < 56, idx >= 456
-            v[q] = make_float2(w * xl[q], w * xr[q]);
+            v[q] = mul2(bcast(w), x[q]);
         }
         if (!(dbg & 8)) fft_forward<9>(v, lane, buf, w0, stw + FftPlan<9>::TW_SMALL_OFFSET);
         __syncwarp();
@@ -396,10 +395,11 @@ __device__ __forceinline__ void spec_column(const float* __restrict__ yl, const 
             const int k = lane + 32 * m;
             const float2 a = buf[nat_idx(k)];
             const float2 bb = buf[nat_idx((SSB_N_FFT - k) & (SSB_N_FFT - 1))];
-            const float lx = a.x + bb.x, ly = a.y - bb.y;      // A + conj(B)
-            const float rx = a.x - bb.x, ry = a.y + bb.y;      // A - conj(B)
-            accl[m] += fast_sqrt(lx * lx + ly * ly);
-            accr[m] += fast_sqrt(rx * rx + ry * ry);
+            const float2 cb = make_float2(bb.x, -bb.y);
+            const float2 l = add2(a, cb), r = sub2(a, cb);     // A + conj(B), A - conj(B)
+            const float2 l2 = mul2(l, l), r2 = mul2(r, r);
+            accl[m] += fast_sqrt(l2.x + l2.y);
+            accr[m] += fast_sqrt(r2.x + r2.y);
         }
         if (lane == 0) {                                       // bin 256 is alone in pooled row 64
             const float2 a = buf[nat_idx(256)];
@@ -409,9 +409,9 @@ __device__ __forceinline__ void spec_column(const float* __restrict__ yl, const 
         __syncwarp();                                          // buf is rewritten by the next frame's exchange
         // slide the sample window by one hop (5 x 32 samples)
 #pragma unroll
-        for (int q = 1; q < 10; ++q) { xl[q] = xl[q + 5]; xr[q] = xr[q + 5]; }
+        for (int q = 1; q < 10; ++q) x[q] = x[q + 5];
 #pragma unroll
-        for (int u = 0; u < 5; ++u) { xl[10 + u] = nl[u]; xr[10 + u] = nr[u]; }
+        for (int u = 0; u < 5; ++u) x[10 + u] = nx[u];
     }
 }
 
