@@ -235,6 +235,15 @@ __device__ __forceinline__ int pad_idx(int l) {
     if constexpr (PADST == 0) return l;
     else return l + PADST * (l / (16 * PADST));
 }
+// pad_idx(pass_pos(t, i, st)) is affine in i: base + i * stride with a compile-time stride, so the 16
+// exchange accesses of a pass use one computed address plus immediates.  (For st >= 16*PADST the i*st term
+// is a whole number of padding periods; the last pass has st == PADST and its 16 elements share one period.)
+template <int PADST>
+__device__ __forceinline__ int pass_base(int t, int st) { return pad_idx<PADST>(pass_pos(t, 0, st)); }
+template <int PADST>
+__host__ __device__ constexpr int pass_stride(int st) {
+    return (PADST > 0 && st >= 16 * PADST) ? st + st / 16 : st;
+}
 
 // barrier among the G consecutive threads that share an exchange region
 template <int G>
@@ -258,11 +267,17 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __re
         const int st = P::stride(p), stp = P::stride(p - 1);
         // exchange: written with pass p-1 layout, read with pass p layout; shared by stp threads
         if (p > 1) { if (stp <= 32) __syncwarp(); else __syncthreads(); }      // previous readers of this region
+        {
+            float2* __restrict__ wp = buf + pass_base<P::PADST>(t, stp);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) buf[pad_idx<P::PADST>(pass_pos(t, i, stp))] = v[i];
+            for (int i = 0; i < 16; ++i) wp[i * pass_stride<P::PADST>(P::stride(p - 1))] = v[i];
+        }
         if (stp <= 32) __syncwarp(); else __syncthreads();
+        {
+            const float2* __restrict__ rp = buf + pass_base<P::PADST>(t, st);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = buf[pad_idx<P::PADST>(pass_pos(t, i, st))];
+            for (int i = 0; i < 16; ++i) v[i] = rp[i * pass_stride<P::PADST>(P::stride(p))];
+        }
         if (st > 1) {
             const Tw6 w = load_tw6<false>(stw + (P::tw_offset(p) - P::TW_SMALL_OFFSET), st, t % st);
             fft16<false, true>(v, w);
@@ -333,11 +348,17 @@ __device__ __forceinline__ void fft_inverse(float2 (&v)[16], int t, float2* __re
         // exchange: written with pass p layout, read with pass p-1 layout; shared by stn threads.
         // The region was last read (previous exchange) by this thread's st-group only.
         if (p < P::NPASS - 1) { if (st <= 32) __syncwarp(); else __syncthreads(); }
+        {
+            float2* __restrict__ wp = buf + pass_base<P::PADST>(t, st);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) buf[pad_idx<P::PADST>(pass_pos(t, i, st))] = v[i];
+            for (int i = 0; i < 16; ++i) wp[i * pass_stride<P::PADST>(P::stride(p))] = v[i];
+        }
         if (stn <= 32) __syncwarp(); else __syncthreads();
+        {
+            const float2* __restrict__ rp = buf + pass_base<P::PADST>(t, stn);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = buf[pad_idx<P::PADST>(pass_pos(t, i, stn))];
+            for (int i = 0; i < 16; ++i) v[i] = rp[i * pass_stride<P::PADST>(P::stride(p - 1))];
+        }
     }
     fft16<true, true>(v, w0);
 }
