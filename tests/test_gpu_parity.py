@@ -296,3 +296,32 @@ def test_savi_pretraining_dataset_quirk():
         ref = ao.savi_dataset_audiogoal(clips[b], rirs[a], sr, index)
         check_wave(wave[k].cpu().numpy(), ref)
         check_spec(spec[k].cpu().numpy(), ao.compute_spectrogram(ref.astype(np.float32)))
+
+
+def test_full_size_c3_head_and_valid():
+    """BASELINE config 3 at full size on one GPU's share and beyond: 16 kHz, 48000-tap RIRs (3 s reverb), 512 envs;
+    "head" mode (1-s clip: only the first 16000 taps matter) and "valid" mode (4-s clip, steady state: all 48000
+    taps).  Spot checks against the oracle + exact zeros for silent / zero-RIR envs."""
+    from soundspaces_b200 import AudioRequest
+    sr, L, B = 16000, 48000, 512
+    r = renderer(sr, L)
+    clip1, clip4 = make_source(80, sr), make_source(81, 4 * sr)
+    s1, s4 = r.add_source(clip1), r.add_source(clip4)
+    rng = np.random.default_rng(5)
+    base = np.stack([make_rir(200 + i, L) for i in range(8)])
+    mix = rng.standard_normal((B, 8)).astype(np.float32) / 3.0
+    rirs = torch.from_numpy(np.einsum("bk,kle->ble", mix, base).astype(np.float32))
+    rirs[7] = 0.0
+    ids = r.set_dense_rir_bank(rirs.cuda())
+    rirs_h = rirs.numpy()
+    for mode, sid, clip, off in (("head", s1, clip1, 0), ("valid", s4, clip4, 3 * sr)):
+        reqs = [AudioRequest(rir=i, source=sid, offset=off, silent=(k == 11)) for k, i in enumerate(ids)]
+        spec, wave = r.render(reqs, want_wave=True)
+        torch.cuda.synchronize()
+        assert spec.shape == (B, 65, 26, 2)
+        spec_h, wave_h = spec.cpu().numpy(), wave.cpu().numpy()
+        for i in (0, 1, 255, 511):
+            ref = ao.compute_audiogoal(clip, rirs_h[i], sr, audio_index=off // sr)
+            check_wave(wave_h[i], ref)
+            check_spec(spec_h[i], ao.compute_spectrogram(ref.astype(np.float32)))
+        assert not wave_h[7].any() and not spec_h[7].any() and not wave_h[11].any() and not spec_h[11].any()
