@@ -55,6 +55,7 @@ extern "C" {
 
 #define SSB_PAD_REFLECT 0       /* librosa < 0.10 default */
 #define SSB_PAD_CONSTANT 1      /* librosa >= 0.10 default */
+#define SSB_LAYOUT_NCHW 0x100   /* OR into pad_mode: emit (2, 65, T') per env instead of the reference's (65, T', 2) */
 
 #define SSB_N_FFT 512           /* nav.py:89-91 */
 #define SSB_HOP 160

@@ -426,7 +426,7 @@ template <bool REFLECT>
 __global__ void __launch_bounds__(32, SPEC_MIN_BLOCKS)
 spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr, int n_frames, int cols,
                    float* __restrict__ out, const float2* __restrict__ tw,
-                   const float* __restrict__ window, int dbg) {
+                   const float* __restrict__ window, int dbg, int nchw) {
     __shared__ float2 xbuf[SPEC_BUF];
     const int lane = threadIdx.x;
     const int col = blockIdx.x;
@@ -446,7 +446,6 @@ spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr
     // pool 4 adjacent bins (lanes): after the two xor-shuffles every lane of a 4-lane group holds the group sum;
     // lane q of the group then finishes rows m = 2q, 2q+1 only (4 log1p per lane instead of 16).
     // scale: 0.5 (ear packing) / 16 (4x4 mean)
-    float* __restrict__ o = out + (((long long)env * SSB_SPEC_ROWS) * cols + col) * 2;
     const int q = lane & 3;
     float ml[2] = {0.f, 0.f}, mr[2] = {0.f, 0.f};
 #pragma unroll
@@ -458,15 +457,29 @@ spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr
         r += __shfl_xor_sync(0xffffffffu, r, 2);
         if (q == (m >> 1)) { ml[m & 1] = l; mr[m & 1] = r; }
     }
+    const float v64l = log1pf(acc64l * (1.0f / 16.0f)), v64r = log1pf(acc64r * (1.0f / 16.0f));
+    if (!nchw) {
+        // reference layout (65, T', 2): ears interleaved (nav.py:98 np.stack(axis=-1))
+        float* __restrict__ o = out + (((long long)env * SSB_SPEC_ROWS) * cols + col) * 2;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int row = (lane >> 2) + 8 * (2 * q + j);
-        *reinterpret_cast<float2*>(o + (long long)row * cols * 2) =
-            make_float2(log1pf(ml[j] * (0.5f / 16.0f)), log1pf(mr[j] * (0.5f / 16.0f)));
+        for (int j = 0; j < 2; ++j) {
+            const int row = (lane >> 2) + 8 * (2 * q + j);
+            *reinterpret_cast<float2*>(o + (long long)row * cols * 2) =
+                make_float2(log1pf(ml[j] * (0.5f / 16.0f)), log1pf(mr[j] * (0.5f / 16.0f)));
+        }
+        if (lane == 0) *reinterpret_cast<float2*>(o + (long long)64 * cols * 2) = make_float2(v64l, v64r);
+    } else {
+        // channels-first (2, 65, T'): what AudioCNN's permute(0, 3, 1, 2) produces (audio_cnn.py:86)
+        float* __restrict__ ol = out + ((long long)env * 2 * SSB_SPEC_ROWS) * cols + col;
+        float* __restrict__ orr = ol + (long long)SSB_SPEC_ROWS * cols;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int row = (lane >> 2) + 8 * (2 * q + j);
+            ol[(long long)row * cols] = log1pf(ml[j] * (0.5f / 16.0f));
+            orr[(long long)row * cols] = log1pf(mr[j] * (0.5f / 16.0f));
+        }
+        if (lane == 0) { ol[(long long)64 * cols] = v64l; orr[(long long)64 * cols] = v64r; }
     }
-    if (lane == 0)
-        *reinterpret_cast<float2*>(o + (long long)64 * cols * 2) =
-            make_float2(log1pf(acc64l * (1.0f / 16.0f)), log1pf(acc64r * (1.0f / 16.0f)));
 }
 
 // ---------------------------------------------------------------------------
@@ -943,8 +956,10 @@ static int spectrogram_checked(ssb_ctx* ctx, int B, const float* d_wave, int64_t
     if (!ctx) return SSB_E_INVALID_ARG;
     if (B == 0) return SSB_OK;
     if (B < 0 || B > 65535 || !d_wave || !d_spec || sr < SSB_N_FFT || wave_stride < sr ||
-        (pad_mode != SSB_PAD_REFLECT && pad_mode != SSB_PAD_CONSTANT))
+        ((pad_mode & ~SSB_LAYOUT_NCHW) != SSB_PAD_REFLECT && (pad_mode & ~SSB_LAYOUT_NCHW) != SSB_PAD_CONSTANT))
         SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_spectrogram_batch: bad arguments (B=%d sr=%d pad_mode=%d)", B, sr, pad_mode);
+    const int nchw = (pad_mode & SSB_LAYOUT_NCHW) ? 1 : 0;
+    pad_mode &= ~SSB_LAYOUT_NCHW;
     const int frames = 1 + sr / SSB_HOP;
     const int cols = ssb_spec_cols(sr);
     dim3 g(cols, B);
@@ -952,10 +967,10 @@ static int spectrogram_checked(ssb_ctx* ctx, int B, const float* d_wave, int64_t
         LaunchTimer lt(ctx, K_SPECTROGRAM, (cudaStream_t)stream);
         if (pad_mode == SSB_PAD_REFLECT)
             spectrogram_kernel<true><<<g, 32, 0, (cudaStream_t)stream>>>(
-                d_wave, (long long)wave_stride, sr, frames, cols, d_spec, ctx->tw[9], ctx->window, ctx->debug);
+                d_wave, (long long)wave_stride, sr, frames, cols, d_spec, ctx->tw[9], ctx->window, ctx->debug, nchw);
         else
             spectrogram_kernel<false><<<g, 32, 0, (cudaStream_t)stream>>>(
-                d_wave, (long long)wave_stride, sr, frames, cols, d_spec, ctx->tw[9], ctx->window, ctx->debug);
+                d_wave, (long long)wave_stride, sr, frames, cols, d_spec, ctx->tw[9], ctx->window, ctx->debug, nchw);
     }
     SSB_CUDA(ctx, cudaGetLastError());
     return SSB_OK;

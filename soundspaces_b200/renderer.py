@@ -290,21 +290,30 @@ class BatchedAudioRenderer:
             self._wave = torch.empty((n, 2, self.sr), dtype=torch.float32, device=self.device)
         return self._hscratch, self._wave[:n]
 
-    def execute(self, batch: PreparedBatch, want_wave: bool = False, out: Optional[torch.Tensor] = None):
+    def execute(self, batch: PreparedBatch, want_wave: bool = False, out: Optional[torch.Tensor] = None,
+                channels_first: bool = False):
         """Run convolution + spectrogram for a prepared batch on the current stream.
         Returns spec (n, 65, T', 2) [, wave (n, 2, sr)] as CUDA tensors.  The waveform buffer is
-        owned by the renderer and overwritten by the next call (clone to keep)."""
+        owned by the renderer and overwritten by the next call (clone to keep).
+
+        ``out`` may be any contiguous CUDA tensor of the right shape, e.g. the rollout-storage slot
+        ``rollouts.observations["spectrogram"][step + 1]`` (ss_baselines/common/rollout_storage.py:88-91):
+        the observation is then written in place and ``insert`` has nothing to copy.
+        ``channels_first=True`` emits (n, 2, 65, T') -- the layout ``AudioCNN.forward`` asks for with
+        ``permute(0, 3, 1, 2)`` (ss_baselines/av_nav/models/audio_cnn.py:86); ``spec.permute(0, 2, 3, 1)`` is
+        then the reference-shaped view and the CNN's permute of it is contiguous for free."""
         n = batch.n
-        spec = out if out is not None else torch.empty((n,) + self.spec_shape, dtype=torch.float32, device=self.device)
+        shape = (n, 2, self.spec_shape[0], self.spec_shape[1]) if channels_first else (n,) + self.spec_shape
+        spec = out if out is not None else torch.empty(shape, dtype=torch.float32, device=self.device)
         if n == 0:
             return (spec, self._scratch(0)[1]) if want_wave else spec
-        if not (spec.is_cuda and spec.is_contiguous() and spec.shape == (n,) + self.spec_shape):
+        if not (spec.is_cuda and spec.is_contiguous() and tuple(spec.shape) == shape and spec.dtype == torch.float32):
             raise ValueError("bad output tensor")
         hs, wave = self._scratch(n)
         self.ctx.check(self.lib.ssb_render_batch(
             self.ctx.handle, C.byref(self.plan), n, batch.reqs_dev.data_ptr(), self._bank.data_ptr(),
-            self._xpool.data_ptr(), hs.data_ptr(), wave.data_ptr(), self.sr, self.pad_mode, spec.data_ptr(),
-            self._stream()), "ssb_render_batch")
+            self._xpool.data_ptr(), hs.data_ptr(), wave.data_ptr(), self.sr,
+            self.pad_mode | (0x100 if channels_first else 0), spec.data_ptr(), self._stream()), "ssb_render_batch")
         return (spec, wave) if want_wave else spec
 
     def render(self, requests: Sequence[AudioRequest], want_wave: bool = False):

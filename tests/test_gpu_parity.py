@@ -325,3 +325,27 @@ def test_full_size_c3_head_and_valid():
             check_wave(wave_h[i], ref)
             check_spec(spec_h[i], ao.compute_spectrogram(ref.astype(np.float32)))
         assert not wave_h[7].any() and not spec_h[7].any() and not wave_h[11].any() and not spec_h[11].any()
+
+
+def test_rollout_ingestion_in_place_and_channels_first():
+    """N2: the observation is written straight into a rollout-storage slot (rollout_storage.py:27-35, :88-91), and
+    optionally channels-first, the layout AudioCNN.forward permutes to (audio_cnn.py:86)."""
+    from soundspaces_b200 import AudioRequest
+    sr, n, T = 16000, 6, 3
+    r = renderer(sr, 6000)
+    src = make_source(8, sr)
+    sid = r.add_source(src)
+    rirs = [make_rir(300 + i, 2000 + 700 * i) for i in range(n)]
+    ids = r.add_rirs(rirs)
+    batch = r.prepare([AudioRequest(rir=i, source=sid) for i in ids])
+    storage = torch.zeros((T + 1, n, 65, 26, 2), device="cuda")            # observations["spectrogram"]
+    ret = r.execute(batch, out=storage[2])
+    assert ret.data_ptr() == storage[2].data_ptr()
+    ref = np.stack([ao.compute_spectrogram(ao.compute_audiogoal(src, rirs[i], sr)) for i in range(n)])
+    torch.cuda.synchronize()
+    check_spec(storage[2].cpu().numpy(), ref)
+    assert not storage[1].any() and not storage[3].any()
+    nchw = r.execute(batch, channels_first=True)
+    assert nchw.shape == (n, 2, 65, 26) and nchw.is_contiguous()
+    assert torch.equal(nchw.permute(0, 2, 3, 1), storage[2])               # bit-identical, reference-shaped view
+    assert nchw.permute(0, 2, 3, 1).permute(0, 3, 1, 2).is_contiguous()    # what AudioCNN.forward feeds Conv2d
