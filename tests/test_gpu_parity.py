@@ -349,3 +349,63 @@ def test_rollout_ingestion_in_place_and_channels_first():
     assert nchw.shape == (n, 2, 65, 26) and nchw.is_contiguous()
     assert torch.equal(nchw.permute(0, 2, 3, 1), storage[2])               # bit-identical, reference-shaped view
     assert nchw.permute(0, 2, 3, 1).permute(0, 3, 1, 2).is_contiguous()    # what AudioCNN.forward feeds Conv2d
+
+
+@pytest.mark.parametrize("log2n,conv_mode", [(12, 0), (13, 1), (14, 0)])
+def test_randomised_requests(log2n, conv_mode):
+    """160 random requests in one batch: arbitrary sample offsets (not block aligned), arbitrary window lengths,
+    wrap-around, ragged RIRs, distractors, silence -- each checked against the oracle's direct formula
+    out[m] = sum_k h[k] x_ext[offset + m - k]."""
+    from scipy.signal import fftconvolve
+    from soundspaces_b200 import AudioRequest
+    sr = 16000
+    r = renderer(sr, 30000, n_terms=2, log2n=log2n)
+    r.set_conv_mode(conv_mode)
+    rng = np.random.default_rng(100 + log2n)
+    clips = [make_source(90 + i, n) for i, n in enumerate((sr, 2 * sr + 123, 5 * sr, 700))]
+    sids = [r.add_source(c) for c in clips]
+    lens = [1, 2, 255, 2047, 2048, 2049, 4096, 8191, 12345, 16000, 16001, 29999, 30000]
+    rirs = [make_rir(400 + i, L) for i, L in enumerate(lens)] + [None]
+    rids = r.add_rirs(rirs)
+
+    def direct(ci, ri, offset, out_samples, wrap):
+        x, h = clips[ci].astype(np.float64), rirs[ri]
+        out = np.zeros((2, sr))
+        if h is None:
+            return out
+        S = len(x)
+        ext = np.concatenate([x, x if wrap else np.zeros(S)])          # one wrap past the end, else zeros
+        seg_end = offset + out_samples
+        src = np.zeros(seg_end)
+        m = min(seg_end, 2 * S)
+        src[:m] = ext[:m]
+        for ch in range(2):
+            y = fftconvolve(src, h[:, ch].astype(np.float64))
+            out[ch, :out_samples] = y[offset: offset + out_samples]
+        return out
+
+    reqs, refs = [], []
+    for _ in range(160):
+        ci, ri = int(rng.integers(len(clips))), int(rng.integers(len(rirs)))
+        S = len(clips[ci])
+        out_samples = int(rng.choice([sr, 4000, 1, 777, 15999]))
+        wrap = bool(rng.integers(2))
+        offset = int(rng.integers(0, S)) if rng.random() < 0.8 else 0
+        if not wrap:
+            offset = min(offset, max(0, S - 1))
+        silent = rng.random() < 0.05
+        req = AudioRequest(rir=rids[ri], source=sids[ci], offset=offset, out_samples=out_samples, wrap=wrap, silent=silent)
+        ref = np.zeros((2, sr)) if silent else direct(ci, ri, offset, out_samples, wrap)
+        if not silent and rng.random() < 0.3:
+            dci, dri = int(rng.integers(len(clips))), int(rng.integers(len(rirs)))
+            req.distractor_source, req.distractor_rir = sids[dci], rids[dri]
+            ref = ref + direct(dci, dri, 0, out_samples, False)        # distractor: full conv of the whole clip, [:out]
+        reqs.append(req)
+        refs.append(ref)
+    spec, wave = r.render(reqs, want_wave=True)
+    torch.cuda.synchronize()
+    spec, wave = spec.cpu().numpy(), wave.cpu().numpy()
+    for i, ref in enumerate(refs):
+        check_wave(wave[i], ref)
+        check_spec(spec[i], ao.compute_spectrogram(wave[i]))          # spectrogram stage on the same waveform
+    r.set_conv_mode(0)
