@@ -202,6 +202,11 @@ def run_reference(args, rank):
 
 # --------------------------------------------------------------------------- GPU arm
 def run_gpu(args, rank, local_rank, world):
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL prints its version there)
+    # are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from soundspaces_b200 import AudioRequest, BatchedAudioRenderer
@@ -347,7 +352,7 @@ def run_gpu(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n} frames of the same C2 workload in {dt:.1f} s, {cores} processes x 1 thread "
                                               "(oracle/audio_oracle.py: scipy.signal.fftconvolve + restated librosa.stft/block_reduce)"}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
