@@ -133,6 +133,30 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm
+def usable_cpus():
+    """Host threads this process may really use: min(sched affinity, cgroup CPU quota)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:                                     # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:                                 # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
+
+
 def _cpu_init():
     for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[k] = "1"
@@ -172,7 +196,7 @@ def run_reference(args, rank):
     """--impl reference: the reference's own CPU algorithm for the path, all host threads."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cpus()
     per_step = max(cores * 8, 64)        # bounded sample per step
     vals = []
     import multiprocessing as mp
@@ -347,7 +371,7 @@ def run_gpu(args, rank, local_rank, world):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
+            cores = usable_cpus()
             v, n, dt = cpu_throughput(cores * args.cpu_frames_per_core, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n} frames of the same C2 workload in {dt:.1f} s, {cores} processes x 1 thread "
