@@ -166,6 +166,9 @@ int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_r
                           const void* d_xpool, void* d_hscratch, float* d_wave, int64_t wave_stride,
                           int pad_mode, float* d_spec, float* h_spec, float* h_wave, int n_chunks, void* stream);
 
+/* bytes the last ssb_render_batch_host call copied host->device and device->host */
+int ssb_host_copy_bytes(const ssb_ctx* ctx, int64_t* h2d, int64_t* d2h);
+
 /* Ambisonic -> binaural decode of a batch of 9-channel (ACN, second order) impulse responses:
  * d_out_rir[env][n][ear] = sum_k sum_tau (R(az_env) a)_k[n - 128 - tau] * hbank[k][ear][tau], n < L,
  * i.e. what scripts/ambisonic_to_binaural.py:14-19 obtains from the closed AmbisonicBinauralizer

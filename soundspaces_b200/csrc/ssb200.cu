@@ -12,7 +12,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/ssb200.h"
@@ -42,6 +44,7 @@ struct ssb_ctx {
     const void* stage_ptr[2];
     cudaEvent_t stage_done[2];
     int stage_next;
+    int64_t last_h2d_bytes, last_d2h_bytes;        // bytes moved by the last ssb_render_batch_host call
     float2* yscratch;                              // [env][block][N] partition sums (transposed MAC)
     size_t yscratch_elems;
     int conv_mode;       // 0: mac_bins + ifft (default), 1: fused mac_ifft
@@ -1045,6 +1048,8 @@ extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, 
     if (n_chunks <= 1) {
         SSB_CUDA(ctx, cudaMemcpyAsync(d_rir_staging, h_rir, (size_t)rir_bytes, cudaMemcpyHostToDevice, st));
         SSB_CUDA(ctx, cudaMemcpyAsync(d_reqs_staging, h_reqs, (size_t)B * sizeof(ssb_req), cudaMemcpyHostToDevice, st));
+        ctx->last_h2d_bytes = rir_bytes + (int64_t)B * (int64_t)sizeof(ssb_req);
+        ctx->last_d2h_bytes = (int64_t)B * (int64_t)spec_row * 4 + (h_wave ? (int64_t)B * 2 * plan->sr * 4 : 0);
         rc = ssb_render_batch(ctx, plan, B, d_reqs_staging, d_rir_staging, d_xpool, d_hscratch, d_wave, wave_stride,
                               pad_mode, d_spec, stream);
         if (rc) return rc;
@@ -1070,13 +1075,17 @@ extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, 
         if (ctx->stage_ptr[i] == (const void*)d_rir_staging || ctx->stage_ptr[i] == (const void*)d_reqs_staging)
             SSB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_h2d, ctx->stage_done[i], 0));
     SSB_CUDA(ctx, cudaMemcpyAsync(d_reqs_staging, h_reqs, (size_t)B * sizeof(ssb_req), cudaMemcpyHostToDevice, ctx->s_h2d));
+    ctx->last_h2d_bytes = (int64_t)B * (int64_t)sizeof(ssb_req);
+    ctx->last_d2h_bytes = (int64_t)B * (int64_t)spec_row * 4 + (h_wave ? (int64_t)B * 2 * plan->sr * 4 : 0);
     const int64_t bank_taps = rir_bytes / (int64_t)sizeof(float2);
     const int per = (B + n_chunks - 1) / n_chunks;
     int c = 0;
     for (int e0 = 0; e0 < B; e0 += per, ++c) {
         const int nb = (B - e0 < per) ? (B - e0) : per;
-        // tap range of the host bank this chunk reads
-        int64_t lo = bank_taps, hi = 0;
+        // tap ranges of the host bank this chunk reads: silent envs and zero-tap terms need no RIR at all
+        // (the reference returns zeros before it even opens the file, simulator.py:610-612); neighbouring
+        // ranges are merged so a chunk costs a handful of copies
+        std::vector<std::pair<int64_t, int64_t>> runs;
         for (int e = e0; e < e0 + nb; ++e) {
             if (h_reqs[e].flags & SSB_FLAG_SILENT) continue;
             for (int term = 0; term < plan->n_terms; ++term) {
@@ -1084,13 +1093,21 @@ extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, 
                 if (ct.rir_taps <= 0) continue;
                 if (ct.rir_offset < 0 || ct.rir_offset + ct.rir_taps > bank_taps)
                     SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_render_batch_host: request %d reads outside the host RIR buffer", e);
-                if (ct.rir_offset < lo) lo = ct.rir_offset;
-                if (ct.rir_offset + ct.rir_taps > hi) hi = ct.rir_offset + ct.rir_taps;
+                runs.emplace_back(ct.rir_offset, ct.rir_offset + ct.rir_taps);
             }
         }
-        if (hi > lo)
+        std::sort(runs.begin(), runs.end());
+        const int64_t kMergeGap = 2048;                         // taps (16 KB): cheaper to copy than to split
+        size_t i0 = 0;
+        while (i0 < runs.size()) {
+            int64_t lo = runs[i0].first, hi = runs[i0].second;
+            size_t i1 = i0 + 1;
+            while (i1 < runs.size() && runs[i1].first <= hi + kMergeGap) { if (runs[i1].second > hi) hi = runs[i1].second; ++i1; }
             SSB_CUDA(ctx, cudaMemcpyAsync(d_rir_staging + 2 * lo, h_rir + 2 * lo, (size_t)(hi - lo) * sizeof(float2),
                                           cudaMemcpyHostToDevice, ctx->s_h2d));
+            ctx->last_h2d_bytes += (hi - lo) * (int64_t)sizeof(float2);
+            i0 = i1;
+        }
         SSB_CUDA(ctx, cudaEventRecord(ctx->ev[2 * c], ctx->s_h2d));
         SSB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[2 * c], 0));
         rc = ssb_render_batch(ctx, plan, nb, d_reqs_staging + e0, d_rir_staging, d_xpool,
@@ -1152,6 +1169,13 @@ extern "C" int ssb_intensity_batch(ssb_ctx* ctx, int B, const float* d_wave, int
     intensity_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(d_wave, (long long)wave_stride, sr, num_frame, d_out);
     ctx->launches += 1;
     SSB_CUDA(ctx, cudaGetLastError());
+    return SSB_OK;
+}
+
+extern "C" int ssb_host_copy_bytes(const ssb_ctx* ctx, int64_t* h2d, int64_t* d2h) {
+    if (!ctx || !h2d || !d2h) return SSB_E_INVALID_ARG;
+    *h2d = ctx->last_h2d_bytes;
+    *d2h = ctx->last_d2h_bytes;
     return SSB_OK;
 }
 

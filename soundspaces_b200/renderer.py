@@ -417,4 +417,7 @@ class HostSession:
             hs.data_ptr(), wave.data_ptr(), r.sr, r.pad_mode, self.d_spec.data_ptr(), self.h_spec.data_ptr(),
             self.h_wave.data_ptr() if self.h_wave is not None else None, self.n_chunks, r._stream()),
             "ssb_render_batch_host")
+        h2d, d2h = C.c_int64(), C.c_int64()
+        r.lib.ssb_host_copy_bytes(r.ctx.handle, C.byref(h2d), C.byref(d2h))
+        self.h2d_bytes, self.d2h_bytes = h2d.value, d2h.value      # what this step really moved (silent envs need no RIR)
         return self.h_spec
