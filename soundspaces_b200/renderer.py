@@ -132,6 +132,17 @@ class BatchedAudioRenderer:
             self._bank_used = need
         return ids
 
+    def reset_bank(self):
+        """Forget every RIR (ids become invalid).  Used by the file-backed service when the resident
+        bank outgrows its budget: the working set of a scene is reloaded on demand."""
+        self._bank_used = 0
+        self._rir_off.clear()
+        self._rir_len.clear()
+
+    @property
+    def bank_bytes(self) -> int:
+        return self._bank_used * 8
+
     def bank_mark(self):
         """Stack mark for transient RIRs (the continuous simulator renders a new RIR every step)."""
         return (self._bank_used, len(self._rir_off))

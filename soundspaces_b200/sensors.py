@@ -205,6 +205,7 @@ class VectorAudioObservations:
     def collect(self, sims) -> torch.Tensor:
         r = self.renderer
         n = len(sims)
+        self.service.maybe_trim()
         out = torch.empty((n,) + r.spec_shape, dtype=torch.float32, device=r.device)
         todo, reqs, keys = [], [], []
         for i, sim in enumerate(sims):

@@ -41,8 +41,9 @@ class AudioRenderService:
     _instances: Dict[tuple, "AudioRenderService"] = {}
 
     def __init__(self, sr: int, device="cuda:0", max_taps: Optional[int] = None, pad_mode: str = "reflect",
-                 n_terms: int = 2, log2n: int = 0):
+                 n_terms: int = 2, log2n: int = 0, max_bank_bytes: int = 16 << 30):
         self.sr = sr
+        self.max_bank_bytes = int(max_bank_bytes)
         # 1-s clips only ever use the first sr taps; multi-second clips need the whole RIR
         self.max_taps = int(max_taps) if max_taps else 4 * sr
         self.renderer = BatchedAudioRenderer(sr, self.max_taps, device=device, n_terms=n_terms, log2n=log2n,
@@ -59,6 +60,14 @@ class AudioRenderService:
         return cls._instances[key]
 
     # -- banks ---------------------------------------------------------------
+    def maybe_trim(self):
+        """Call between steps (never while requests are being built): when the resident RIR bank exceeds
+        its budget, drop it; files are re-read on demand (the full dataset is 867 GB, a scene's working
+        set is what has to stay resident)."""
+        if self.renderer.bank_bytes > self.max_bank_bytes:
+            self.renderer.reset_bank()
+            self._rir_ids.clear()
+
     def rir_from_file(self, path: str) -> int:
         rid = self._rir_ids.get(path)
         if rid is None:
@@ -150,6 +159,7 @@ class B200AudioMixin:
     # -- reference API ---------------------------------------------------------
     def _compute_audiogoal(self):
         sr = self.config.AUDIO.RIR_SAMPLING_RATE
+        self._b200_service().maybe_trim()
         req = self._b200_request()
         if req.silent:
             logging.debug('Step count is greater than duration. Empty spectrogram.')
@@ -182,6 +192,7 @@ class B200AudioMixin:
                 return np.zeros(r.spec_shape)              # float64 zeros, as the reference on silence
             spec = r.spectrogram(torch.from_numpy(np.asarray(wave, dtype=np.float32)).to(r.device))
             return spec[0].cpu().numpy()
+        self._b200_service().maybe_trim()
         req = self._b200_request()
         if req.silent:
             if use_cache:

@@ -201,3 +201,24 @@ def test_vector_batching_and_batch_obs(tmp_path):
         assert np.allclose(out[i].cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
     batch = batch_obs([{"spectrogram": out[i], "x": np.float32(i)} for i in range(n)], device=out.device)
     assert batch["spectrogram"].is_cuda and torch.equal(batch["spectrogram"], out)
+
+
+def test_rir_bank_budget_trim(tmp_path):
+    """The file-backed bank is dropped between steps when it outgrows its budget and refilled on demand."""
+    from soundspaces_b200.simulator import AudioRenderService
+    sr = 16000
+    src = make_source(4, sr)
+    d = str(tmp_path)
+    rirs = [make_rir(30 + i, 4000) for i in range(4)]
+    for i in range(4):
+        write_rir(d, "replica", "apartment_0", 0, i, 1, sr, rirs[i])
+    svc = AudioRenderService(sr, max_bank_bytes=2 * 4000 * 8 + 1)       # room for two RIRs
+    outs = []
+    for i in range(4):
+        sim = make_sim(d, sr, {"telephone.wav": src}, receiver=i)
+        sim._b200_svc = svc
+        outs.append(sim.get_current_audiogoal_observation())
+        assert svc.renderer.bank_bytes <= 3 * 4000 * 8
+    for i in range(4):
+        ref = ao.compute_audiogoal(src, rirs[i], sr)
+        assert np.abs(outs[i] - ref).max() <= 1e-4 * np.abs(ref).max()
