@@ -13,6 +13,7 @@ PyTorch is used for device memory and streams only; all arithmetic runs in
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from dataclasses import dataclass
 from typing import Optional, Sequence
@@ -49,6 +50,13 @@ class AudioRequest:
     silent: bool = False           # simulator.py:610-612
     distractor_rir: Optional[int] = None   # simulator.py:649-664
     distractor_source: Optional[int] = None
+    # transient RIR supplied inline ((L, 2) array; overrides ``rir``): the RIR habitat-sim renders every step
+    # (simulator.py:626, continuous_simulator.py:419).  Uploaded for the one call and dropped afterwards.
+    rir_array: Optional[object] = None
+
+
+class _PoolReset(Exception):
+    """The window-spectra pool was recycled while a batch was being prepared."""
 
 
 @dataclass
@@ -245,10 +253,12 @@ class BatchedAudioRenderer:
         if self._xpool_used + need > self._xpool.numel() // 2:
             if need > self._xpool.numel() // 2:
                 raise RuntimeError("window-spectra pool too small for one clip; raise xpool_bytes")
-            # simplest policy: drop every cached set (they are recomputed on demand)
+            # simplest policy: drop every cached set (they are recomputed on demand).  Offsets handed out
+            # earlier in the current prepare() are stale now: signal it to restart.
             torch.cuda.current_stream(self.device).synchronize()
             self._xcache.clear()
             self._xpool_used = 0
+            raise _PoolReset()
         x_off = self._xpool_used
         src = self._sources[source]
         self.ctx.check(self.lib.ssb_source_windows(
@@ -259,6 +269,8 @@ class BatchedAudioRenderer:
         return self._xcache[key]
 
     def _fill_term(self, term, rir_id, source, offset, wrap, out_samples):
+        if rir_id is not None and rir_id >= len(self._rir_len):
+            raise ValueError(f"unknown RIR id {rir_id}")
         if rir_id is None or rir_id < 0 or self._rir_len[rir_id] == 0:
             term["rir_taps"] = 0
             return
@@ -274,6 +286,17 @@ class BatchedAudioRenderer:
 
     # ----------------------------------------------------------------- render
     def prepare(self, requests: Sequence[AudioRequest]) -> PreparedBatch:
+        """Resolve requests into the device request array.  A PreparedBatch stays valid until the
+        window-spectra pool is recycled (only when it overflows) or the RIR bank is reset."""
+        try:
+            return self._prepare(requests)
+        except _PoolReset:
+            try:
+                return self._prepare(requests)            # pool is empty now: the whole batch must fit
+            except _PoolReset:
+                raise RuntimeError("window-spectra pool too small for this batch; raise xpool_bytes") from None
+
+    def _prepare(self, requests: Sequence[AudioRequest]) -> PreparedBatch:
         n = len(requests)
         reqs = np.zeros(n, dtype=REQ_DTYPE)
         for i, r in enumerate(requests):
@@ -327,17 +350,47 @@ class BatchedAudioRenderer:
             self.pad_mode | (0x100 if channels_first else 0), spec.data_ptr(), self._stream()), "ssb_render_batch")
         return (spec, wave) if want_wave else spec
 
+    @contextlib.contextmanager
+    def _inline_rirs(self, *request_lists):
+        """Upload the inline (transient) RIRs of one call behind a bank mark and drop them afterwards."""
+        inline, seen = [], set()
+        for reqs in request_lists:
+            for r in reqs:
+                if r is not None and r.rir_array is not None and not getattr(r, "_inline_live", False) \
+                        and id(r) not in seen:
+                    inline.append(r)
+                    seen.add(id(r))
+        if not inline:
+            yield
+            return
+        mark = self.bank_mark()
+        saved = [r.rir for r in inline]
+        try:
+            ids = self.add_rirs([np.asarray(r.rir_array, dtype=np.float32) for r in inline])
+            for r, i in zip(inline, ids):
+                r.rir = i
+                r._inline_live = True                     # nested calls (render_crossfade -> convolve) reuse the upload
+            yield
+        finally:
+            for r, old in zip(inline, saved):
+                r.rir = old
+                r._inline_live = False
+            self.bank_release(mark)                       # later uploads are stream-ordered after the kernels
+
     def render(self, requests: Sequence[AudioRequest], want_wave: bool = False):
-        return self.execute(self.prepare(requests), want_wave=want_wave)
+        with self._inline_rirs(requests):
+            return self.execute(self.prepare(requests), want_wave=want_wave)
 
     def convolve(self, requests: Sequence[AudioRequest]) -> torch.Tensor:
         """Waveforms only: (n, 2, sr) -- ``get_current_audiogoal_observation`` for a batch."""
-        batch = self.prepare(requests)
-        hs, wave = self._scratch(batch.n)
-        if batch.n:
-            self.ctx.check(self.lib.ssb_convolve_batch(
-                self.ctx.handle, C.byref(self.plan), batch.n, batch.reqs_dev.data_ptr(), self._bank.data_ptr(),
-                self._xpool.data_ptr(), hs.data_ptr(), wave.data_ptr(), self.sr, self._stream()), "ssb_convolve_batch")
+        with self._inline_rirs(requests):
+            batch = self.prepare(requests)
+            hs, wave = self._scratch(batch.n)
+            if batch.n:
+                self.ctx.check(self.lib.ssb_convolve_batch(
+                    self.ctx.handle, C.byref(self.plan), batch.n, batch.reqs_dev.data_ptr(), self._bank.data_ptr(),
+                    self._xpool.data_ptr(), hs.data_ptr(), wave.data_ptr(), self.sr, self._stream()),
+                    "ssb_convolve_batch")
         return wave
 
     def render_crossfade(self, cur: Sequence[AudioRequest], prev: Sequence[Optional[AudioRequest]],
@@ -347,6 +400,10 @@ class BatchedAudioRenderer:
         n = len(cur)
         enable = torch.tensor([p is not None for p in prev], dtype=torch.uint8, device=self.device)
         prev_reqs = [p if p is not None else c for p, c in zip(prev, cur)]
+        with self._inline_rirs(cur, prev):
+            return self._render_crossfade(cur, prev_reqs, enable, n, want_wave)
+
+    def _render_crossfade(self, cur, prev_reqs, enable, n, want_wave):
         w_prev = self.convolve(prev_reqs)
         if self._prev_wave is None or self._prev_wave.shape[0] < n:
             self._prev_wave = torch.empty((n, 2, self.sr), dtype=torch.float32, device=self.device)

@@ -86,10 +86,6 @@ class AudioRenderService:
             self._rir_ids[path] = rid
         return rid
 
-    def rir_from_array(self, rir) -> int:
-        """Transient RIR (continuous simulator: rendered by habitat-sim every step)."""
-        return self.renderer.add_rirs([np.asarray(rir, dtype=np.float32)])[0]
-
     def source(self, key, samples) -> int:
         """Device copy of a decoded clip, memoised per array object (the reference memoises the
         decoded clip per sound name in ``_source_sound_dict``, simulator.py:595-600; keying on the
@@ -136,10 +132,10 @@ class B200AudioMixin:
         sr = self.config.AUDIO.RIR_SAMPLING_RATE
         if self._episode_step_count > self._duration:
             return AudioRequest(rir=-1, source=0, silent=True)
+        rid, inline = -1, None
         if not self.config.USE_RENDERED_OBSERVATIONS:
-            # simulator.py:626 (RIR rendered by habitat-sim); kept resident like the file RIRs
-            rir = np.transpose(np.array(self._sim.get_sensor_observations()["audio_sensor"]))
-            rid = svc.rir_from_array(rir)
+            # simulator.py:626: RIR rendered by habitat-sim for this step -> transient, supplied inline
+            inline = np.transpose(np.array(self._sim.get_sensor_observations()["audio_sensor"]))
         else:
             rid = svc.rir_from_file(self._b200_rir_path(self._source_position_index))
         clip = self.current_source_sound
@@ -149,7 +145,7 @@ class B200AudioMixin:
             index = self._audio_index
             self._audio_index = (self._audio_index + 1) % self._audio_length
             offset = index * sr
-        req = AudioRequest(rir=rid, source=sid, offset=offset)
+        req = AudioRequest(rir=rid, source=sid, offset=offset, rir_array=inline)
         if self.config.AUDIO.HAS_DISTRACTOR_SOUND:
             dclip = self._source_sound_dict[self._current_distractor_sound]
             req.distractor_source = svc.source(self._current_distractor_sound, dclip)
@@ -236,10 +232,10 @@ class B200ContinuousAudioMixin:
         sid = svc.source(self._current_sound, clip)
         kw = dict(source=sid, offset=int(self._current_sample_index), out_samples=num_sample, wrap=True)
         cur_rir = np.transpose(np.array(self._prev_sim_obs["audio_sensor"]))
-        cur = AudioRequest(rir=svc.rir_from_array(cur_rir), **kw)
+        cur = AudioRequest(rir=-1, rir_array=cur_rir, **kw)
         prev = None
         if self.config.AUDIO.CROSSFADE and self._last_rir is not None:
-            prev = AudioRequest(rir=svc.rir_from_array(self._last_rir), **kw)
+            prev = AudioRequest(rir=-1, rir_array=self._last_rir, **kw)
         return cur, prev
 
     def _compute_audiogoal(self):
@@ -248,15 +244,11 @@ class B200ContinuousAudioMixin:
             logging.debug('Step count is greater than duration. Empty spectrogram.')
             return np.zeros((2, sr))
         r = self._b200_service().renderer
-        mark = r.bank_mark()
-        try:
-            cur, prev = self._b200_requests()
-            if prev is None:
-                return r.convolve([cur])[0].cpu().numpy()
-            _, wave = r.render_crossfade([cur], [prev], want_wave=True)
-            return wave[0].cpu().numpy()
-        finally:
-            r.bank_release(mark)
+        cur, prev = self._b200_requests()
+        if prev is None:
+            return r.convolve([cur])[0].cpu().numpy()
+        _, wave = r.render_crossfade([cur], [prev], want_wave=True)
+        return wave[0].cpu().numpy()
 
     def get_current_audiogoal_observation(self):
         return self._compute_audiogoal()
@@ -267,13 +259,9 @@ class B200ContinuousAudioMixin:
         r = self._b200_service().renderer
         if self._episode_step_count > self._duration:
             return np.zeros(r.spec_shape)
-        mark = r.bank_mark()
-        try:
-            cur, prev = self._b200_requests()
-            spec = r.render([cur]) if prev is None else r.render_crossfade([cur], [prev])
-            return spec[0].cpu().numpy()
-        finally:
-            r.bank_release(mark)
+        cur, prev = self._b200_requests()
+        spec = r.render([cur]) if prev is None else r.render_crossfade([cur], [prev])
+        return spec[0].cpu().numpy()
 
 
 _DISCRETE = ("_compute_audiogoal", "get_current_audiogoal_observation", "get_current_spectrogram_observation",

@@ -409,3 +409,24 @@ def test_randomised_requests(log2n, conv_mode):
         check_wave(wave[i], ref)
         check_spec(spec[i], ao.compute_spectrogram(wave[i]))          # spectrogram stage on the same waveform
     r.set_conv_mode(0)
+
+
+def test_window_pool_recycling():
+    """A tiny window-spectra pool is recycled mid-batch; prepare() restarts and results stay correct."""
+    from soundspaces_b200 import AudioRequest, BatchedAudioRenderer
+    sr = 16000
+    r = BatchedAudioRenderer(sr, 8192, device="cuda:0", xpool_bytes=1)      # minimum pool: 64 windows
+    clip = make_source(33, 6 * sr)
+    sid = r.add_source(clip)
+    rir = make_rir(34, 5000)
+    rid = r.add_rirs([rir])[0]
+    for rep in range(3):
+        offs = [sr * k + 37 * rep for k in range(5)]
+        reqs = [AudioRequest(rir=rid, source=sid, offset=o) for o in offs]
+        wave = r.convolve(reqs)
+        torch.cuda.synchronize()
+        x = clip.astype(np.float64)
+        from scipy.signal import fftconvolve
+        for k, o in enumerate(offs):
+            full = np.stack([fftconvolve(x[: o + sr], rir[:, ch].astype(np.float64)) for ch in range(2)])
+            check_wave(wave[k].cpu().numpy(), full[:, o: o + sr])
