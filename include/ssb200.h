@@ -120,7 +120,7 @@ int ssb_set_conv_mode(ssb_ctx* ctx, int mode);
 int ssb_set_streams(ssb_ctx* ctx, int n);
 
 /* Profiling only: ablation switches (1 skip the spectrum MAC, 2 skip the inverse FFT, 4 skip the
- * waveform loads of the spectrogram kernel, 8 skip its FFT).  Results are wrong when non-zero. */
+ * waveform loads of the spectrogram kernel, 8 skip its FFT, 32 force the direct-form SH decode).  Results are wrong when non-zero. */
 int ssb_set_debug(ssb_ctx* ctx, int flags);
 
 /* Fill a plan.  log2n = 0 picks the default (12). */

@@ -45,6 +45,8 @@ struct ssb_ctx {
     cudaEvent_t stage_done[2];
     int stage_next;
     int64_t last_h2d_bytes, last_d2h_bytes;        // bytes moved by the last ssb_render_batch_host call
+    float2* gscratch;                              // [env][9][4096] SH-decode filter spectra
+    size_t gscratch_elems;
     float2* yscratch;                              // [env][block][N] partition sums (transposed MAC)
     size_t yscratch_elems;
     int conv_mode;       // 0: mac_bins + ifft (default), 1: fused mac_ifft
@@ -567,6 +569,76 @@ sh_decode_kernel(const float* __restrict__ amb, int L, const float2* __restrict_
     }
 }
 
+// FFT version of the same decode (default for long responses): overlap-save with N = 4096 blocks.  The filters are
+// 384 taps long including their 128-sample delay, so a block yields N - 384 = 3712 valid outputs (91 % efficient,
+// against 50 % for the uniformly partitioned RIR convolution).  Per block: 9 forward transforms of the (real)
+// ambisonic channels, multiply-accumulate with the 9 filter spectra G_k = FFT(delayed g_k) (both ears packed:
+// real input x complex filter = left + i right), one inverse transform.  7x fewer flops than the direct form.
+constexpr int SHF_LOG2N = 12;
+constexpr int SHF_F = SH_DELAY + SH_TAPS;                          // 384
+constexpr int SHF_HOP = (1 << SHF_LOG2N) - SHF_F;                  // 3712
+
+// grid (9, B); block 256: G[env][k][slot]
+__global__ void __launch_bounds__(FftPlan<SHF_LOG2N>::T)
+sh_filter_fft_kernel(const float2* __restrict__ g, float2* __restrict__ G, const float2* __restrict__ tw) {
+    using P = FftPlan<SHF_LOG2N>;
+    extern __shared__ float2 smem[];
+    float2* stw = smem + P::SMEM_ELEMS;
+    const int k = blockIdx.x, env = blockIdx.y, t = threadIdx.x;
+    const Tw6 w0 = load_tw6<true>(tw, P::T, t);
+    stage_small_twiddles<SHF_LOG2N>(stw, tw, t);
+    const float2* __restrict__ gk = g + ((long long)env * SH_CH + k) * SH_TAPS;
+    float2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int n = t + q * P::T;
+        v[q] = (n >= SH_DELAY && n < SHF_F) ? __ldg(gk + n - SH_DELAY) : make_float2(0.f, 0.f);
+    }
+    fft_forward<SHF_LOG2N>(v, t, smem, w0, stw);
+    store_slots<SHF_LOG2N>(G + ((long long)env * SH_CH + k) * P::N, v, t);
+}
+
+// grid (ceil(L / SHF_HOP), B); block 256
+__global__ void __launch_bounds__(FftPlan<SHF_LOG2N>::T, 2)
+sh_ols_kernel(const float* __restrict__ amb, int L, const float2* __restrict__ G, float* __restrict__ out,
+              const float2* __restrict__ tw) {
+    using P = FftPlan<SHF_LOG2N>;
+    extern __shared__ float2 smem[];
+    float2* stw = smem + P::SMEM_ELEMS;
+    const int b = blockIdx.x, env = blockIdx.y, t = threadIdx.x;
+    const Tw6 w0 = load_tw6<true>(tw, P::T, t);
+    stage_small_twiddles<SHF_LOG2N>(stw, tw, t);
+    const long long base = (long long)b * SHF_HOP - SHF_F;          // first input sample of this block's window
+    const float* __restrict__ a = amb + (long long)env * L * SH_CH;
+    const float2* __restrict__ Ge = G + (long long)env * SH_CH * P::N + t;
+    float2 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int k = 0; k < SH_CH; ++k) {
+        float2 v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const long long n = base + t + q * P::T;
+            v[q] = make_float2((n >= 0 && n < L) ? __ldg(a + n * SH_CH + k) : 0.f, 0.f);
+        }
+        if (k > 0) __syncthreads();                                 // the exchange buffer is reused by the next transform
+        fft_forward<SHF_LOG2N>(v, t, smem, w0, stw);
+        const float2* __restrict__ gk = Ge + (long long)k * P::N;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = cfma(v[i], __ldg(gk + i * P::T), acc[i]);
+    }
+    __syncthreads();
+    fft_inverse<SHF_LOG2N>(acc, t, smem, tw, stw);
+    constexpr float scale = 1.0f / (float)P::N;
+    float2* __restrict__ o = reinterpret_cast<float2*>(out) + (long long)env * L;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int nl = t + q * P::T;                                // valid outputs: nl >= 384
+        const long long n = (long long)b * SHF_HOP + nl - SHF_F;
+        if (nl >= SHF_F && n < L) o[n] = make_float2(acc[q].x * scale, acc[q].y * scale);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------
@@ -729,6 +801,7 @@ extern "C" void ssb_destroy(ssb_ctx* ctx) {
         if (ctx->tw[l]) cudaFree(ctx->tw[l]);
     if (ctx->window) cudaFree(ctx->window);
     if (ctx->yscratch) cudaFree(ctx->yscratch);
+    if (ctx->gscratch) cudaFree(ctx->gscratch);
     if (ctx->s_comp[0]) {
         for (int i = 0; i < SSB_MAX_STREAMS; ++i) { cudaStreamDestroy(ctx->s_comp[i]); cudaEventDestroy(ctx->ev_comp[i]); }
         cudaEventDestroy(ctx->ev_fork);
@@ -1153,6 +1226,30 @@ extern "C" int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int 
     }
     sh_filters_kernel<<<B, SH_TAPS, 0, st>>>(d_hbank, d_az_deg, (float2*)d_filters);
     SSB_CUDA(ctx, cudaGetLastError());
+    if (L >= 2 * SHF_HOP && !(ctx->debug & 32)) {
+        // FFT path: filter spectra (context-owned scratch), then overlap-save blocks
+        using P = FftPlan<SHF_LOG2N>;
+        const size_t need = (size_t)B * SH_CH * P::N;
+        if (need > ctx->gscratch_elems) {
+            if (ctx->gscratch) { cudaDeviceSynchronize(); cudaFree(ctx->gscratch); ctx->gscratch = nullptr; ctx->gscratch_elems = 0; }
+            SSB_CUDA(ctx, cudaMalloc(&ctx->gscratch, need * sizeof(float2)));
+            ctx->gscratch_elems = need;
+        }
+        const size_t fsmem = (P::SMEM_ELEMS + P::TW_SMALL_ELEMS) * sizeof(float2);
+        static bool fattr = false;
+        if (!fattr) {
+            SSB_CUDA(ctx, cudaFuncSetAttribute(sh_filter_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            SSB_CUDA(ctx, cudaFuncSetAttribute(sh_ols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            fattr = true;
+        }
+        sh_filter_fft_kernel<<<dim3(SH_CH, B), P::T, fsmem, st>>>((const float2*)d_filters, ctx->gscratch, ctx->tw[SHF_LOG2N]);
+        SSB_CUDA(ctx, cudaGetLastError());
+        sh_ols_kernel<<<dim3((L + SHF_HOP - 1) / SHF_HOP, B), P::T, fsmem, st>>>(d_amb, L, ctx->gscratch, d_out_rir,
+                                                                              ctx->tw[SHF_LOG2N]);
+        ctx->launches += 3;
+        SSB_CUDA(ctx, cudaGetLastError());
+        return SSB_OK;
+    }
     dim3 g((L + SH_TILE - 1) / SH_TILE, B);
     sh_decode_kernel<<<g, SH_THREADS, smem, st>>>(d_amb, L, (const float2*)d_filters, d_out_rir);
     ctx->launches += 2;

@@ -74,6 +74,21 @@ def test_cuda_sh_decode_matches_oracle_and_tool(shg):
         lti = so.sh_decode(amb[i], az[i], shg["bank"])
         assert np.abs(out[i] - lti).max() <= 1e-4 * np.abs(lti).max()                     # vs the LTI restatement
         assert np.abs(out[i] - shg[f"{n}/out"]).max() <= 5e-3 * np.abs(shg[f"{n}/out"]).max()   # vs the tool itself
+    # long responses take the FFT (overlap-save) path: against the oracle and against the direct-form kernel
+    rng = np.random.default_rng(6)
+    for L in (7424, 9001, 20000):
+        amb_l = (rng.standard_normal((3, L, 9)) * np.exp(-np.arange(L) / (L / 4.0))[None, :, None] * 0.2).astype(np.float32)
+        az_l = [0.0, 45.0, 270.0]
+        fft_out = r.sh_decode(torch.from_numpy(amb_l), az_l).cpu().numpy()
+        r.lib.ssb_set_debug(r.ctx.handle, 32)                       # force the direct form
+        fir_out = r.sh_decode(torch.from_numpy(amb_l), az_l).cpu().numpy()
+        r.lib.ssb_set_debug(r.ctx.handle, 0)
+        for i in range(3):
+            lti = so.sh_decode(amb_l[i], az_l[i], shg["bank"])
+            peak = np.abs(lti).max()
+            assert np.abs(fft_out[i] - lti).max() <= 1e-4 * peak
+            assert np.abs(fir_out[i] - lti).max() <= 1e-4 * peak
+            assert np.abs(fft_out[i] - fir_out[i]).max() <= 1e-5 * peak
     # ragged length (not a multiple of the tile) and a long IR
     rng = np.random.default_rng(3)
     long_amb = (rng.standard_normal((2, 5003, 9)) * 0.2).astype(np.float32)
