@@ -20,7 +20,8 @@ for log2n in (12, 13, 14):
         r.intensity(wave)
         torch.cuda.synchronize()
 r = BatchedAudioRenderer(16000, 4096)
-r.sh_decode(torch.randn(2, 1500, 9), [10.0, 200.0])
+r.sh_decode(torch.randn(2, 1500, 9), [10.0, 200.0])          # direct form
+r.sh_decode(torch.randn(2, 7600, 9), [10.0, 200.0])          # overlap-save FFT form
 r.set_streams(2)
 sid = r.add_source(make_source(3, 16000))
 ids = r.add_rirs([make_rir(i, 3000) for i in range(64)])
