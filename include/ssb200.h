@@ -123,7 +123,7 @@ int ssb_set_streams(ssb_ctx* ctx, int n);
  * waveform loads of the spectrogram kernel, 8 skip its FFT, 32 force the direct-form SH decode).  Results are wrong when non-zero. */
 int ssb_set_debug(ssb_ctx* ctx, int flags);
 
-/* Fill a plan.  log2n = 0 picks the default (12). */
+/* Fill a plan.  log2n = 0 picks the default (12; 13 when max_taps > 24576). */
 int ssb_make_plan(ssb_ctx* ctx, int sr, int max_taps, int n_terms, int log2n, ssb_plan* plan);
 
 /* spectrogram geometry: frames = 1 + sr/160, cols = ceil(frames/4) */

@@ -872,7 +872,9 @@ extern "C" int ssb_spec_cols(int sr) {
 
 extern "C" int ssb_make_plan(ssb_ctx* ctx, int sr, int max_taps, int n_terms, int log2n, ssb_plan* plan) {
     if (!ctx || !plan) return SSB_E_INVALID_ARG;
-    if (log2n == 0) log2n = 12;
+    // default block size: N = 4096 keeps 4 CTAs per SM and the finest tiling; beyond ~12 partitions the per-bin
+    // partition sums dominate and N = 8192 is the better plan (measured at config 3)
+    if (log2n == 0) log2n = max_taps > 24576 ? 13 : 12;
     if (log2n < 12 || !log2_supported(log2n)) SSB_FAIL(ctx, SSB_E_INVALID_ARG, "log2n %d unsupported (12, 13, 14)", log2n);
     if (sr < SSB_N_FFT || max_taps < 0 || n_terms < 1 || n_terms > 2)
         SSB_FAIL(ctx, SSB_E_INVALID_ARG, "bad plan arguments sr=%d max_taps=%d n_terms=%d", sr, max_taps, n_terms);
