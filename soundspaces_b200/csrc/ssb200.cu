@@ -329,10 +329,11 @@ mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
 // ---------------------------------------------------------------------------
 constexpr int SPEC_BUF = 512 + 32;
 
-// sqrt.approx.f32: one MUFU, max relative error 2^-23 (the IEEE sqrtf expands to ~8 instructions)
+// sqrt.approx.ftz.f32: one MUFU, max relative error 2^-23 (IEEE sqrtf expands to ~8 instructions, the
+// non-ftz approx form to 4: range test + two scalings around the MUFU for denormal inputs)
 __device__ __forceinline__ float fast_sqrt(float x) {
     float y;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
