@@ -296,6 +296,44 @@ def run_gpu(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
 
+    # ---- optional centralised-policy mode: every step ends with ONE in-place all-gather of the
+    # observation batch; the spectrogram kernel writes straight into this rank's slice of the gather buffer
+    gather_info = None
+    if world > 1:
+        try:
+            from soundspaces_b200.distributed import GatheredObservations
+            gobs = GatheredObservations(B * world, r.spec_shape, rank, world, dev)
+            assert gobs.n_local == B
+
+            def gstep(i):
+                r.execute(batches[i % N_BANKS], out=gobs.local)
+                return gobs.gather()
+
+            for i in range(max(3, args.warmup // 2)):
+                gstep(i)
+            barrier()
+            ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ge0.record()
+            for i in range(args.steps):
+                flat = gstep(i)
+            ge1.record()
+            barrier()
+            tg = torch.tensor([ge0.elapsed_time(ge1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            # every rank must now hold every rank's rows: compare a checksum of the gathered batch across ranks
+            chk = flat.double().sum().reshape(1)
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            gather_info = {"value": B * world * args.steps / (float(tg.item()) * 1e-3), "unit": UNIT,
+                           "ms_per_step": float(tg.item()) / args.steps,
+                           "bytes_sent_per_rank_per_step": int(gobs.local.numel() * 4),
+                           "collective": "one in-place ncclAllGather per step (all_gather_into_tensor on the buffer the "
+                                         "spectrogram kernel wrote into)",
+                           "identical_on_all_ranks": bool(float(lo.item()) == float(hi.item()))}
+        except Exception as e:          # informational leg: never take the headline measurement down with it
+            gather_info = {"error": repr(e)[:200]}
+
     # ---- per-kernel durations for the roofline (same K steps, events around every launch)
     r.ctx.set_kernel_timing(True)
     for i in range(args.steps):
@@ -370,6 +408,8 @@ def run_gpu(args, rank, local_rank, world):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if gather_info is not None:
+            line["with_allgather"] = gather_info
         if world == 1 and not args.no_cpu:
             cores = usable_cpus()
             v, n, dt = cpu_throughput(cores * args.cpu_frames_per_core, cores)

@@ -25,6 +25,8 @@
  *                              of the reference hands over), copies included
  *   ssb_sh_decode_batch     <- scripts/ambisonic_to_binaural.py:14-19 (closed AmbisonicBinauralizer ELF)
  *   ssb_intensity_batch     <- Intensity.get_observation, ss_baselines/av_wan/avwan_sensors.py:91-100
+ *   ssb_logmel_batch        <- EXTENSION (no reference code): the log-mel front end BASELINE.json configs[2] names;
+ *                              log1p(librosa.feature.melspectrogram) on the reference's STFT geometry (nav.py:89-92)
  *   ssb_pcm16_decode/encode <- int16 <-> float32 PCM (librosa.load decode used at
  *                              simulator.py:597; np.int16(audio*32767) at
  *                              scripts/interactive_demo.py:110)
@@ -183,6 +185,17 @@ int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int L, const fl
  * the clip maximum. */
 int ssb_intensity_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int num_frame,
                         float* d_out, void* stream);
+
+/* EXTENSION -- the reference has no mel front end; BASELINE.json configs[2] asks for one.
+ * d_out[env][j][t][ear] = log1p(sum_k M[j][k] * |STFT(d_wave[env][ear])[k][t]|^power), power 1 or 2, t < 1 + sr/160,
+ * STFT as in ssb_spectrogram_batch (n_fft 512, hop 160, Hann(400), centre padding per pad_mode), M the Slaney
+ * filterbank of librosa.filters.mel(sr, 512, n_mels) with fmin 0, fmax sr/2 (n_mels <= 64), i.e.
+ * log1p(librosa.feature.melspectrogram(y, sr, n_fft=512, hop_length=160, win_length=400, n_mels, power)).
+ * ssb_mel_filterbank writes that matrix densely, [n_mels][257], to HOST memory (needs no device). */
+int ssb_logmel_frames(int sr);
+int ssb_mel_filterbank(int sr, int n_mels, float* h_out);
+int ssb_logmel_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int n_mels, int power,
+                     int pad_mode, float* d_out, void* stream);
 
 /* PCM helpers.  decode: float32(x) / 32768 (exact).  encode mode 0: round(x*32768) saturated;
  * mode 1: trunc(x*32767) saturated (interactive_demo.py:110). */

@@ -228,6 +228,58 @@ def savi_dataset_audiogoal(source, rir, sr, index):
 
 
 # --------------------------------------------------------------------------
+# log-mel EXTENSION (no reference code: BASELINE.json configs[2] names a log-mel front end, the reference has
+# none -- SURVEY.md 8(d)).  Restates librosa as published: ``filters.mel`` (Slaney scale, norm='slaney') and
+# ``feature.melspectrogram`` (mel_basis @ abs(stft)**power), followed by the reference's own ``np.log1p``
+# compression (nav.py:97).  PARITY UNPINNED (librosa is not installable here); the filterbank is
+# triangulated against ``torchaudio.functional.melscale_fbanks`` in tests/test_logmel.py.
+# --------------------------------------------------------------------------
+def hz_to_mel(f):
+    """librosa.hz_to_mel(htk=False): linear below 1 kHz (200/3 Hz per mel), log above (step log(6.4)/27)."""
+    f = np.asanyarray(f, dtype=np.float64)
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, np.log(6.4) / 27.0
+    return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep, f / f_sp)
+
+
+def mel_to_hz(m):
+    """librosa.mel_to_hz(htk=False)."""
+    m = np.asanyarray(m, dtype=np.float64)
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_filterbank(sr, n_fft=N_FFT, n_mels=64):
+    """``librosa.filters.mel(sr=sr, n_fft=n_fft, n_mels=n_mels)`` (fmin=0, fmax=sr/2, htk=False, norm='slaney',
+    dtype=float32) -> (n_mels, 1 + n_fft//2)."""
+    weights = np.zeros((n_mels, 1 + n_fft // 2), dtype=np.float32)
+    fftfreqs = np.fft.rfftfreq(n=n_fft, d=1.0 / sr)
+    mel_f = mel_to_hz(np.linspace(hz_to_mel(0.0), hz_to_mel(sr / 2.0), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = np.subtract.outer(mel_f, fftfreqs)
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        weights[i] = np.maximum(0, np.minimum(lower, upper))
+    enorm = 2.0 / (mel_f[2: n_mels + 2] - mel_f[:n_mels])
+    weights *= enorm[:, np.newaxis]
+    return weights
+
+
+def logmel(audio_data, sr, n_mels=64, power=2, pad_mode="reflect"):
+    """(2, S) waveform -> (n_mels, 1 + S//160, 2): per ear ``log1p(mel_filterbank @ abs(stft)**power)``, i.e.
+    ``np.log1p(librosa.feature.melspectrogram(y=ear, sr=sr, n_fft=512, hop_length=160, win_length=400,
+    n_mels=n_mels, power=power))`` on the STFT geometry of nav.py:89-92."""
+    fb = mel_filterbank(sr, N_FFT, n_mels)
+    ears = []
+    for ch in range(2):
+        S = np.abs(librosa_stft(np.asarray(audio_data[ch]), pad_mode=pad_mode)) ** power
+        ears.append(np.log1p(fb @ S))
+    return np.stack(ears, axis=-1)
+
+
+# --------------------------------------------------------------------------
 # PCM helpers (A1: librosa.load -> soundfile decode; interactive_demo.py:110)
 # --------------------------------------------------------------------------
 def pcm16_to_float32(x):

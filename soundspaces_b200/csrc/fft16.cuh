@@ -257,7 +257,10 @@ __device__ __forceinline__ void group_barrier() {
 //     caller so the loads can be issued early.
 // stw: table of passes >= 1 (pass p at FftPlan::tw_offset(p) - TW_SMALL_OFFSET), normally in shared memory.
 // buf: >= SMEM_ELEMS float2, private to the group; the caller orders other uses of buf.
-template <int LOG2N>
+// LANE_STAGE = false leaves out the final radix-M stage across lanes: the caller folds it into its own
+// reads (the STFT kernel does, for M = 2: lane 2a then holds P_a[i], lane 2a+1 holds Q_a[i], and
+// X[a + 16 i] = P + Q, X[a + 16 i + N/2] = P - Q).
+template <int LOG2N, bool LANE_STAGE = true>
 __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __restrict__ buf, const Tw6& w0,
                                             const float2* __restrict__ stw) {
     using P = FftPlan<LOG2N>;
@@ -286,7 +289,9 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __re
         }
     }
     // leftover radix-M across M adjacent lanes (DIF)
-    if constexpr (P::M == 2) {
+    if constexpr (!LANE_STAGE) {
+        return;
+    } else if constexpr (P::M == 2) {
         const float sgn = (t & 1) ? -1.f : 1.f;                // lower lane: v + o, upper lane: o - v  (one FFMA each)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {

@@ -22,6 +22,15 @@
 
 using namespace ssb;
 
+// Device-side ablation switches (ssb_set_debug bits 1, 2, 4, 8: skip the partition sums / inverse FFT / sample
+// loads / STFT) cost branches and a register in the hot kernels, so they only exist in -DSSB_ABLATION builds
+// (scratch/ablate.py); in the product build the kernels see a constant 0.
+#ifdef SSB_ABLATION
+#define SSB_DBG(x) (x)
+#else
+#define SSB_DBG(x) 0
+#endif
+
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
@@ -54,6 +63,9 @@ struct ssb_ctx {
     cudaStream_t s_comp[SSB_MAX_STREAMS];
     cudaEvent_t ev_comp[SSB_MAX_STREAMS], ev_fork;
     int debug;           // ablation switches for profiling (ssb_set_debug); 0 in production
+    // mel filterbanks by (sr, n_mels), built on first use (ssb_logmel_batch)
+    struct MelBank { int sr, n_mels; int2* rows; int* ofs; float* w; };
+    std::vector<MelBank>* mel;
     std::vector<TimedLaunch>* timed;
     char err[512];
 };
@@ -178,8 +190,13 @@ fwd_src_kernel(const float* __restrict__ src, int S, long long m0, int wrap, int
 // partition for every block: 4.9 MB per env at config 2 against 0.26 + 0.70 MB here); repeated
 // touches of the same slot column are L1 hits.  grid (N / 256, B); block 256.
 // ---------------------------------------------------------------------------
+#ifdef MACB_MIN_BLOCKS
+#define MACB_BOUNDS __launch_bounds__(256, MACB_MIN_BLOCKS)
+#else
+#define MACB_BOUNDS __launch_bounds__(256)
+#endif
 template <int LOG2N, int NPMAX, int NBMAX>
-__global__ void __launch_bounds__(256)
+__global__ void MACB_BOUNDS
 mac_bins_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpool, const float2* __restrict__ H,
                 int max_parts, int n_terms, long long h_elems_per_env, float2* __restrict__ Y, int n_blocks, int sr) {
     using P = FftPlan<LOG2N>;
@@ -246,13 +263,17 @@ mac_bins_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
 // multiply-accumulate over partitions + inverse FFT + emit
 // grid (B, n_blocks); block T.
 // ---------------------------------------------------------------------------
+#ifndef IFFT12_MIN_BLOCKS
+#define IFFT12_MIN_BLOCKS 5      // resident CTAs per SM asked of ptxas for the N = 4096 instance
+#endif
 template <int LOG2N, bool FROM_Y>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::T)
+__global__ void __launch_bounds__(FftPlan<LOG2N>::T, (LOG2N == 12 && FROM_Y) ? IFFT12_MIN_BLOCKS : 1)
 mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpool,
                 const float2* __restrict__ H, int max_parts, int n_terms, long long h_elems_per_env,
                 float* __restrict__ wave, long long wave_stride, int sr,
-                const float2* __restrict__ tw, int dbg) {
+                const float2* __restrict__ tw, int dbg_arg) {
     using P = FftPlan<LOG2N>;
+    const int dbg = SSB_DBG(dbg_arg);
     extern __shared__ float2 smem[];
     float2* stw = smem + P::SMEM_ELEMS;
     constexpr int PART = P::N / 2;
@@ -328,6 +349,13 @@ mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
 // over the 4 frames in registers, pooled over 4 bins with two shuffles, log1p, store.
 // ---------------------------------------------------------------------------
 constexpr int SPEC_BUF = 512 + 32;
+#ifndef SPEC_UNROLL
+#define SPEC_UNROLL 1            // frames of a pooled column unrolled (1, 2 or 4)
+#endif
+constexpr int kSpecUnroll = SPEC_UNROLL;
+#ifndef SPEC_FOLD_R2
+#define SPEC_FOLD_R2 1           // 1: fold the STFT's last radix-2 (lane) stage into the magnitude reads
+#endif
 
 // sqrt.approx.ftz.f32: one MUFU, max relative error 2^-23 (IEEE sqrtf expands to ~8 instructions, the
 // non-ftz approx form to 4: range test + two scalings around the MUFU for denormal inputs)
@@ -363,22 +391,28 @@ __device__ __forceinline__ void spec_column(const float* __restrict__ yl, const 
                                             float (&accl)[8], float (&accr)[8], float& acc64l, float& acc64r, int dbg) {
     const Tw6 w0 = load_tw6<true>(stw, 32, lane);
     const int n0 = col * SSB_POOL * SSB_HOP - SSB_N_FFT / 2 + lane;          // sample of x_0 for this lane
+    // interior columns: every sample is a fixed offset from these two pointers (immediates once the frame loop is unrolled)
+    const float* __restrict__ pl = yl + n0;
+    const float* __restrict__ pr = yr + n0;
     float2 x[15];                                                            // window of the current frame: (L, R) pairs, q = 1..14
 #pragma unroll
-    for (int q = 1; q < 15; ++q)
-        x[q] = (dbg & 4) ? make_float2(0.f, 0.f)
-                         : make_float2(spec_sample<REFLECT, INTERIOR>(yl, n0 + 32 * q, sr),
-                                       spec_sample<REFLECT, INTERIOR>(yr, n0 + 32 * q, sr));
-#pragma unroll 1
+    for (int q = 1; q < 15; ++q) {
+        if (INTERIOR) x[q] = make_float2(__ldg(pl + 32 * q), __ldg(pr + 32 * q));
+        else x[q] = (dbg & 4) ? make_float2(0.f, 0.f)
+                              : make_float2(spec_sample<REFLECT, false>(yl, n0 + 32 * q, sr),
+                                            spec_sample<REFLECT, false>(yr, n0 + 32 * q, sr));
+    }
+#pragma unroll kSpecUnroll
     for (int fr = 0; fr < SSB_POOL; ++fr) {
         // prefetch the 5 new samples of the next frame (j = 15 + 5 fr ..); latency hides behind this frame's FFT
         float2 nx[5];
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
-            const int n = n0 + 32 * (15 + 5 * fr + u);
+            const int j = 15 + 5 * fr + u;
             const bool need = fr + 1 < SSB_POOL && !(dbg & 4);
-            nx[u] = need ? make_float2(spec_sample<REFLECT, INTERIOR>(yl, n, sr), spec_sample<REFLECT, INTERIOR>(yr, n, sr))
-                         : make_float2(0.f, 0.f);
+            if (INTERIOR) nx[u] = fr + 1 < SSB_POOL ? make_float2(__ldg(pl + 32 * j), __ldg(pr + 32 * j)) : make_float2(0.f, 0.f);
+            else nx[u] = need ? make_float2(spec_sample<REFLECT, false>(yl, n0 + 32 * j, sr), spec_sample<REFLECT, false>(yr, n0 + 32 * j, sr))
+                              : make_float2(0.f, 0.f);
         }
         const bool f_ok = INTERIOR || (col * SSB_POOL + fr < n_frames);     // frames past the end add 0 (block_reduce pads with 0)
         float2 v[16];
@@ -389,6 +423,37 @@ __device__ __forceinline__ void spec_column(const float* __restrict__ yl, const 
             const float w = f_ok ? __ldg(swin + lane + 32 * q) : 0.f;  // centre-padded Hann: 0 for idx < 56, idx >= 456
             v[q] = mul2(bcast(w), x[q]);
         }
+#if SPEC_FOLD_R2
+        // The last radix-2 stage (across lane pairs) is folded into the reads below: lane 2a holds P_a[i], lane
+        // 2a+1 holds Q_a[i], Z[kap] = P[kap] + Q[kap] and Z[kap + 256] = P[kap] - Q[kap] for kap = a + 16 i.
+        // P goes to the lower half of buf, Q to the upper half -- the same addresses the finished spectrum used.
+        fft_forward<9, false>(v, lane, buf, w0, stw + FftPlan<9>::TW_SMALL_OFFSET);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) buf[nat_idx((lane >> 1) + 16 * i + 256 * (lane & 1))] = v[i];
+        __syncwarp();
+        // Z = FFT(w*(yL + i yR)):  XL[k] = (Z[k] + conj Z[N-k])/2,  XR[k] = (Z[k] - conj Z[N-k])/(2i);
+        // for 0 < k < 256: Z[N-k] = Z[(256-k) + 256] = P[256-k] - Q[256-k]; Z[N-0] = Z[0]
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int k = lane + 32 * m;
+            const int kk = (256 - k) & 255;
+            const float2 a = add2(buf[nat_idx(k)], buf[nat_idx(256 + k)]);
+            float2 bb;
+            if (m == 0) bb = fma2(bcast(lane == 0 ? 1.f : -1.f), buf[nat_idx(256 + kk)], buf[nat_idx(kk)]);
+            else bb = sub2(buf[nat_idx(kk)], buf[nat_idx(256 + kk)]);
+            const float2 cb = make_float2(bb.x, -bb.y);
+            const float2 l = add2(a, cb), r = sub2(a, cb);     // A + conj(B), A - conj(B)
+            const float2 l2 = mul2(l, l), r2 = mul2(r, r);
+            accl[m] += fast_sqrt(l2.x + l2.y);
+            accr[m] += fast_sqrt(r2.x + r2.y);
+        }
+        if (lane == 0) {                                       // bin 256 = P[0] - Q[0] is alone in pooled row 64
+            const float2 a = sub2(buf[nat_idx(0)], buf[nat_idx(256)]);
+            acc64l += fabsf(a.x);
+            acc64r += fabsf(a.y);
+        }
+#else
         if (!(dbg & 8)) fft_forward<9>(v, lane, buf, w0, stw + FftPlan<9>::TW_SMALL_OFFSET);
         __syncwarp();
         // natural order: k = (lane>>1) + 16 i + 256 (lane&1)
@@ -412,6 +477,7 @@ __device__ __forceinline__ void spec_column(const float* __restrict__ yl, const 
             acc64l += fabsf(a.x);
             acc64r += fabsf(a.y);
         }
+#endif
         __syncwarp();                                          // buf is rewritten by the next frame's exchange
         // slide the sample window by one hop (5 x 32 samples)
 #pragma unroll
@@ -432,8 +498,9 @@ template <bool REFLECT>
 __global__ void __launch_bounds__(32, SPEC_MIN_BLOCKS)
 spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr, int n_frames, int cols,
                    float* __restrict__ out, const float2* __restrict__ tw,
-                   const float* __restrict__ window, int dbg, int nchw) {
+                   const float* __restrict__ window, int dbg_arg, int nchw) {
     __shared__ float2 xbuf[SPEC_BUF];
+    const int dbg = SSB_DBG(dbg_arg);
     const int lane = threadIdx.x;
     const int col = blockIdx.x;
     const int env = blockIdx.y;
@@ -485,6 +552,113 @@ spectrogram_kernel(const float* __restrict__ wave, long long wave_stride, int sr
             orr[(long long)row * cols] = log1pf(mr[j] * (0.5f / 16.0f));
         }
         if (lane == 0) { ol[(long long)64 * cols] = v64l; orr[(long long)64 * cols] = v64r; }
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// log-mel spectrogram.  EXTENSION: BASELINE.json configs[2] and the north star name a log-mel front end, the
+// reference itself has none; defined here as
+//     out[env][j][t][ear] = log1p( sum_k M[j][k] * |STFT(wave[env][ear])[k][t]|^power ),   power in {1, 2},
+// with the reference's STFT (n_fft 512, hop 160, Hann(400), centre padding: nav.py:89-92) and M the Slaney
+// mel filterbank of librosa.filters.mel(sr, 512, n_mels) (area-normalised triangles, fmin 0, fmax sr/2), i.e.
+// log1p(librosa.feature.melspectrogram(...)) -- the same log1p compression the reference applies (nav.py:97).
+// One warp per group of 4 consecutive frames (the sample window slides exactly as in spec_column).  The
+// filterbank is a sparse matrix -- every bin feeds at most two triangles, 2 * 257 non-zeros in all against
+// 64 * 257 = 16448 dense entries -- so it is applied as per-mel sparse dot products from shared memory; a dense
+// tensor-core GEMM would first have to write the (257, T) power spectra to HBM (2 x 284 KB per env at
+// 44.1 kHz, more than every other byte this path moves) to do 32x the arithmetic.
+// ---------------------------------------------------------------------------
+constexpr int MEL_MAX = 64;                  // two mel rows per lane
+constexpr int MEL_PBUF = SSB_N_FFT / 2 + 1;  // 257 bins
+
+template <bool REFLECT>
+__global__ void __launch_bounds__(32, 16)
+logmel_kernel(const float* __restrict__ wave, long long wave_stride, int sr, int n_frames, int n_mels, int power,
+              float* __restrict__ out, const float2* __restrict__ tw, const float* __restrict__ window,
+              const int2* __restrict__ mel_rows /* (first bin, count) */, const int* __restrict__ mel_ofs,
+              const float* __restrict__ mel_w) {
+    __shared__ float2 buf[SPEC_BUF];
+    __shared__ float2 pbuf[MEL_PBUF + 1];
+    const int lane = threadIdx.x;
+    const int t0 = blockIdx.x * SSB_POOL;                       // first frame of this warp
+    const int env = blockIdx.y;
+    const float* __restrict__ yl = wave + (long long)env * 2 * wave_stride;
+    const float* __restrict__ yr = yl + wave_stride;
+    const Tw6 w0 = load_tw6<true>(tw, 32, lane);
+    const int n0 = t0 * SSB_HOP - SSB_N_FFT / 2 + lane;
+    float2 x[15];
+#pragma unroll
+    for (int q = 1; q < 15; ++q)
+        x[q] = make_float2(spec_sample<REFLECT, false>(yl, n0 + 32 * q, sr), spec_sample<REFLECT, false>(yr, n0 + 32 * q, sr));
+    // this lane's mel rows j = lane and lane + 32
+    int2 row[2];
+    const float* __restrict__ wrow[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        row[h] = j < n_mels ? __ldg(mel_rows + j) : make_int2(0, 0);
+        wrow[h] = mel_w + (j < n_mels ? __ldg(mel_ofs + j) : 0);
+    }
+    float2 res[2][SSB_POOL];
+#pragma unroll 1
+    for (int fr = 0; fr < SSB_POOL; ++fr) {
+        float2 nx[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int n = n0 + 32 * (15 + 5 * fr + u);
+            nx[u] = fr + 1 < SSB_POOL ? make_float2(spec_sample<REFLECT, false>(yl, n, sr), spec_sample<REFLECT, false>(yr, n, sr))
+                                      : make_float2(0.f, 0.f);
+        }
+        float2 v[16];
+        v[0] = make_float2(0.f, 0.f);
+        v[15] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 1; q < 15; ++q) v[q] = mul2(bcast(__ldg(window + lane + 32 * q)), x[q]);
+        fft_forward<9>(v, lane, buf, w0, tw + FftPlan<9>::TW_SMALL_OFFSET);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) buf[nat_idx((lane >> 1) + 16 * i + 256 * (lane & 1))] = v[i];
+        __syncwarp();
+        // XL[k] = (Z[k] + conj Z[N-k]) / 2, XR[k] = (Z[k] - conj Z[N-k]) / (2i)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int k = lane + 32 * m;
+            const float2 a = buf[nat_idx(k)];
+            const float2 bb = buf[nat_idx((SSB_N_FFT - k) & (SSB_N_FFT - 1))];
+            const float2 cb = make_float2(bb.x, -bb.y);
+            const float2 l = add2(a, cb), r = sub2(a, cb);
+            const float2 l2 = mul2(l, l), r2 = mul2(r, r);
+            const float pl2 = l2.x + l2.y, pr2 = r2.x + r2.y;        // 4 |X|^2
+            pbuf[k] = power == 2 ? make_float2(0.25f * pl2, 0.25f * pr2) : make_float2(0.5f * fast_sqrt(pl2), 0.5f * fast_sqrt(pr2));
+        }
+        if (lane == 0) {                                              // Nyquist bin: Z[256] = XL[256] + i XR[256], both real
+            const float2 a = buf[nat_idx(256)];
+            pbuf[256] = power == 2 ? make_float2(a.x * a.x, a.y * a.y) : make_float2(fabsf(a.x), fabsf(a.y));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float2 acc = make_float2(0.f, 0.f);
+            for (int i = 0; i < row[h].y; ++i) acc = fma2(bcast(__ldg(wrow[h] + i)), pbuf[row[h].x + i], acc);
+            res[h][fr] = acc;
+        }
+        __syncwarp();                                                 // buf / pbuf are rewritten by the next frame
+#pragma unroll
+        for (int q = 1; q < 10; ++q) x[q] = x[q + 5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) x[10 + u] = nx[u];
+    }
+    // out[env][j][t][ear]: 4 consecutive frames of one mel row are 32 contiguous bytes
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        if (j >= n_mels) continue;
+        float* __restrict__ o = out + (((long long)env * n_mels + j) * n_frames + t0) * 2;
+#pragma unroll
+        for (int fr = 0; fr < SSB_POOL; ++fr)
+            if (t0 + fr < n_frames)
+                *reinterpret_cast<float2*>(o + 2 * fr) = make_float2(log1pf(res[h][fr].x), log1pf(res[h][fr].y));
     }
 }
 
@@ -766,6 +940,7 @@ extern "C" int ssb_create(int device, ssb_ctx** out) {
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
     ctx->timed = new (std::nothrow) std::vector<TimedLaunch>();
+    ctx->mel = new (std::nothrow) std::vector<ssb_ctx::MelBank>();
     *out = ctx;   // returned even on failure so that ssb_last_error works; caller destroys
     SSB_CUDA(ctx, cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -818,6 +993,10 @@ extern "C" void ssb_destroy(ssb_ctx* ctx) {
     if (ctx->timed) {
         for (auto& tl : *ctx->timed) { cudaEventDestroy(tl.a); cudaEventDestroy(tl.b); }
         delete ctx->timed;
+    }
+    if (ctx->mel) {
+        for (auto& mb : *ctx->mel) { cudaFree(mb.rows); cudaFree(mb.ofs); cudaFree(mb.w); }
+        delete ctx->mel;
     }
     delete ctx;
 }
@@ -1256,6 +1435,108 @@ extern "C" int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int 
     dim3 g((L + SH_TILE - 1) / SH_TILE, B);
     sh_decode_kernel<<<g, SH_THREADS, smem, st>>>(d_amb, L, (const float2*)d_filters, d_out_rir);
     ctx->launches += 2;
+    SSB_CUDA(ctx, cudaGetLastError());
+    return SSB_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// log-mel host side: the Slaney filterbank of librosa.filters.mel(sr, n_fft=512, n_mels, fmin=0, fmax=sr/2,
+// htk=False, norm='slaney'), built in double precision, rounded like librosa (float32 triangle, then
+// float32(triangle * enorm)) and stored row-sparse.
+// ---------------------------------------------------------------------------
+static double hz_to_mel_slaney(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz_slaney(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+// row-sparse filterbank: rows[j] = (first bin, count), ofs[j] = index of the row's first weight in w
+static void build_mel_rows(int sr, int n_mels, std::vector<int2>& rows, std::vector<int>& ofs, std::vector<float>& w) {
+    const int n_bins = SSB_N_FFT / 2 + 1;
+    std::vector<double> mel_f(n_mels + 2);
+    const double m_lo = hz_to_mel_slaney(0.0), m_hi = hz_to_mel_slaney(0.5 * (double)sr);
+    const double step = (m_hi - m_lo) / (double)(n_mels + 1);
+    for (int i = 0; i < n_mels + 2; ++i)        // np.linspace(m_lo, m_hi, n_mels + 2)
+        mel_f[i] = mel_to_hz_slaney(i == n_mels + 1 ? m_hi : (double)i * step + m_lo);
+    rows.assign(n_mels, make_int2(0, 0));
+    ofs.assign(n_mels, 0);
+    w.clear();
+    std::vector<float> rw(n_bins);
+    for (int j = 0; j < n_mels; ++j) {
+        const double enorm = 2.0 / (mel_f[j + 2] - mel_f[j]);
+        int first = -1, last = -1;
+        for (int k = 0; k < n_bins; ++k) {
+            const double f = (double)k * ((double)sr / (double)SSB_N_FFT);       // librosa.fft_frequencies(sr, n_fft)
+            const double lower = -(mel_f[j] - f) / (mel_f[j + 1] - mel_f[j]);
+            const double upper = (mel_f[j + 2] - f) / (mel_f[j + 2] - mel_f[j + 1]);
+            const float tri = (float)fmax(0.0, fmin(lower, upper));             // weights[i] is float32 ...
+            rw[k] = (float)((double)tri * enorm);                               // ... `weights *= enorm` rounds once more
+            if (rw[k] != 0.f) { if (first < 0) first = k; last = k; }
+        }
+        if (first >= 0) rows[j] = make_int2(first, last - first + 1);
+        ofs[j] = (int)w.size();
+        for (int k = 0; k < rows[j].y; ++k) w.push_back(rw[rows[j].x + k]);
+    }
+    if (w.empty()) w.push_back(0.f);
+}
+
+// host only (no device needed): dense [n_mels][257] copy of the filterbank the kernels use
+extern "C" int ssb_mel_filterbank(int sr, int n_mels, float* h_out) {
+    if (sr < SSB_N_FFT || n_mels < 1 || n_mels > MEL_MAX || !h_out) return SSB_E_INVALID_ARG;
+    std::vector<int2> rows; std::vector<int> ofs; std::vector<float> w;
+    build_mel_rows(sr, n_mels, rows, ofs, w);
+    const int n_bins = SSB_N_FFT / 2 + 1;
+    for (int j = 0; j < n_mels; ++j) {
+        for (int k = 0; k < n_bins; ++k) h_out[j * n_bins + k] = 0.f;
+        for (int i = 0; i < rows[j].y; ++i) h_out[j * n_bins + rows[j].x + i] = w[ofs[j] + i];
+    }
+    return SSB_OK;
+}
+
+static int get_mel_bank(ssb_ctx* ctx, int sr, int n_mels, const ssb_ctx::MelBank** out) {
+    for (auto& mb : *ctx->mel)
+        if (mb.sr == sr && mb.n_mels == n_mels) { *out = &mb; return SSB_OK; }
+    std::vector<int2> rows; std::vector<int> ofs; std::vector<float> w;
+    build_mel_rows(sr, n_mels, rows, ofs, w);
+    ssb_ctx::MelBank mb{sr, n_mels, nullptr, nullptr, nullptr};
+    SSB_CUDA(ctx, cudaMalloc(&mb.rows, rows.size() * sizeof(int2)));
+    SSB_CUDA(ctx, cudaMalloc(&mb.ofs, ofs.size() * sizeof(int)));
+    SSB_CUDA(ctx, cudaMalloc(&mb.w, w.size() * sizeof(float)));
+    SSB_CUDA(ctx, cudaMemcpy(mb.rows, rows.data(), rows.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    SSB_CUDA(ctx, cudaMemcpy(mb.ofs, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SSB_CUDA(ctx, cudaMemcpy(mb.w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->mel->push_back(mb);
+    *out = &ctx->mel->back();
+    return SSB_OK;
+}
+
+extern "C" int ssb_logmel_frames(int sr) { return 1 + sr / SSB_HOP; }
+
+extern "C" int ssb_logmel_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int n_mels, int power,
+                                int pad_mode, float* d_out, void* stream) {
+    if (!ctx) return SSB_E_INVALID_ARG;
+    if (B == 0) return SSB_OK;
+    if (B < 0 || B > 65535 || !d_wave || !d_out || sr < SSB_N_FFT || wave_stride < sr || n_mels < 1 || n_mels > MEL_MAX ||
+        (power != 1 && power != 2) || (pad_mode != SSB_PAD_REFLECT && pad_mode != SSB_PAD_CONSTANT) || ((uintptr_t)d_out & 7))
+        SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_logmel_batch: bad arguments (B=%d sr=%d n_mels=%d power=%d pad_mode=%d)", B, sr,
+                 n_mels, power, pad_mode);
+    const ssb_ctx::MelBank* mb = nullptr;
+    int rc = get_mel_bank(ctx, sr, n_mels, &mb);
+    if (rc) return rc;
+    const int frames = ssb_logmel_frames(sr);
+    dim3 g((frames + SSB_POOL - 1) / SSB_POOL, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pad_mode == SSB_PAD_REFLECT)
+        logmel_kernel<true><<<g, 32, 0, st>>>(d_wave, (long long)wave_stride, sr, frames, n_mels, power, d_out, ctx->tw[9],
+                                               ctx->window, mb->rows, mb->ofs, mb->w);
+    else
+        logmel_kernel<false><<<g, 32, 0, st>>>(d_wave, (long long)wave_stride, sr, frames, n_mels, power, d_out, ctx->tw[9],
+                                                ctx->window, mb->rows, mb->ofs, mb->w);
+    ctx->launches += 1;
     SSB_CUDA(ctx, cudaGetLastError());
     return SSB_OK;
 }

@@ -27,3 +27,40 @@ def gather_observations(local: torch.Tensor, n_envs: int, rank: int, world: int)
     # rank r, slot k  ->  env k*world + r
     out = out.view(world, per, *local.shape[1:]).transpose(0, 1).reshape(world * per, *local.shape[1:])
     return out[:n_envs]
+
+
+class GatheredObservations:
+    """The all-gather target as a pre-allocated buffer the kernels write into ("fuse by having
+    the last kernel write directly into the rank's slice of the pre-registered gather buffer").
+
+    ``buffer`` is ``(world, per_rank, *row_shape)``; rank r passes ``local`` -- the contiguous view
+    ``buffer[r]`` -- as ``out=`` to ``BatchedAudioRenderer.execute`` so the spectrogram kernel's stores ARE the
+    send buffer, and ``gather()`` is then one in-place ``all_gather_into_tensor`` (NCCL's in-place form:
+    send pointer = receive pointer + rank * count; no staging copy, no padding copy).  Rows come back in
+    rank-major order; ``env_ids`` maps row -> env for the ``i -> rank i mod G`` sharding and ``in_env_order()``
+    gives the permuted copy when a consumer insists on env order."""
+
+    def __init__(self, n_envs: int, row_shape, rank: int, world: int, device, dtype=torch.float32):
+        self.n_envs, self.rank, self.world = int(n_envs), int(rank), int(world)
+        self.per = -(-self.n_envs // self.world)
+        self.buffer = torch.zeros((self.world, self.per) + tuple(row_shape), dtype=dtype, device=device)
+        ids = torch.arange(self.world * self.per).view(self.world, self.per)
+        self.env_ids = (ids % self.per) * self.world + ids // self.per          # row (r, k) holds env k*world + r
+        self.n_local = len(shard_envs(self.n_envs, self.rank, self.world))
+
+    @property
+    def local(self) -> torch.Tensor:
+        """This rank's slice, ``(n_local, *row_shape)``: hand it to the renderer as ``out=``."""
+        return self.buffer[self.rank, : self.n_local]
+
+    def gather(self) -> torch.Tensor:
+        """In-place all-gather; returns the ``(world * per_rank, *row_shape)`` rank-major view of the buffer."""
+        flat = self.buffer.view((self.world * self.per,) + tuple(self.buffer.shape[2:]))
+        if self.world > 1:
+            dist.all_gather_into_tensor(flat, self.buffer[self.rank])
+        return flat
+
+    def in_env_order(self) -> torch.Tensor:
+        flat = self.buffer.view((self.world * self.per,) + tuple(self.buffer.shape[2:]))
+        order = torch.argsort(self.env_ids.reshape(-1))[: self.n_envs]
+        return flat[order.to(flat.device)]

@@ -429,6 +429,35 @@ class BatchedAudioRenderer:
                        "ssb_spectrogram_batch")
         return spec
 
+    # ------------------------------------------------------------- log-mel (extension)
+    def logmel_shape(self, n_mels: int = 64):
+        """(n_mels, 1 + sr//160, 2)."""
+        return (int(n_mels), self.lib.ssb_logmel_frames(self.sr), 2)
+
+    def logmel(self, wave: torch.Tensor, n_mels: int = 64, power: int = 2, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """EXTENSION (the reference has no mel front end; BASELINE.json configs[2] names one): per ear
+        ``log1p(librosa.feature.melspectrogram(y, sr, n_fft=512, hop_length=160, win_length=400, n_mels, power))``
+        on the reference's STFT geometry (nav.py:89-92) for a (n, 2, sr) CUDA batch -> (n, n_mels, 1 + sr//160, 2)."""
+        if wave.ndim == 2:
+            wave = wave[None]
+        if not (wave.is_cuda and wave.dtype == torch.float32 and wave.shape[1] == 2 and wave.shape[2] == self.sr):
+            raise ValueError(f"expected CUDA float32 (n, 2, {self.sr})")
+        wave = wave.contiguous()
+        n = wave.shape[0]
+        shape = (n,) + self.logmel_shape(n_mels)
+        res = out if out is not None else torch.empty(shape, dtype=torch.float32, device=self.device)
+        if not (res.is_cuda and res.is_contiguous() and tuple(res.shape) == shape and res.dtype == torch.float32):
+            raise ValueError("bad output tensor")
+        self.ctx.check(self.lib.ssb_logmel_batch(self.ctx.handle, n, wave.data_ptr(), self.sr, self.sr, int(n_mels),
+                                                 int(power), self.pad_mode, res.data_ptr(), self._stream()),
+                       "ssb_logmel_batch")
+        return res
+
+    def render_logmel(self, requests: Sequence[AudioRequest], n_mels: int = 64, power: int = 2,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Convolution (every reference branch, as :meth:`convolve`) followed by :meth:`logmel`."""
+        return self.logmel(self.convolve(requests), n_mels=n_mels, power=power, out=out)
+
     # --------------------------------------------------------- host-buffer path
     def make_host_session(self, n: int, taps: int, want_wave: bool = False, n_chunks: int = 4):
         """Pinned host buffers + device staging for the host-buffer entry (the e2e path)."""

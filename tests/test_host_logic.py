@@ -120,6 +120,17 @@ def _gloo_worker(rank, world, port, tmp):
     full = gather_observations(local, n_envs, rank, world)
     assert full.shape == (n_envs, 65, 3, 2)
     assert all(float(full[i, 0, 0, 0]) == float(i) for i in range(n_envs))
+    # the same through the pre-allocated gather buffer the kernels write into (in-place all-gather)
+    from soundspaces_b200.distributed import GatheredObservations
+    g = GatheredObservations(n_envs, (65, 3, 2), rank, world, "cpu")
+    assert g.local.is_contiguous() and g.local.shape[0] == len(mine)
+    g.local.copy_(local)                                    # stands for execute(out=g.local)
+    flat = g.gather()
+    assert flat.data_ptr() == g.buffer.data_ptr()           # no staging copy
+    for row, env in enumerate(g.env_ids.reshape(-1).tolist()):
+        if env < n_envs:
+            assert float(flat[row, 0, 0, 0]) == float(env)
+    assert torch.equal(g.in_env_order(), full)
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
