@@ -299,7 +299,7 @@ def run_gpu(args, rank, local_rank, world):
     # ---- optional centralised-policy mode: every step ends with ONE in-place all-gather of the
     # observation batch; the spectrogram kernel writes straight into this rank's slice of the gather buffer
     gather_info = None
-    if world > 1:
+    if world > 1 and args.gather:
         try:
             from soundspaces_b200.distributed import GatheredObservations
             gobs = GatheredObservations(B * world, r.spec_shape, rank, world, dev)
@@ -432,6 +432,8 @@ def main():
     ap.add_argument("--conv-mode", type=int, default=0, help="0: mac_bins + ifft kernels, 1: fused mac_ifft")
     ap.add_argument("--chunks", type=int, default=2, help="pipeline depth of the host-buffer (e2e) entry")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gather", action="store_true",
+                    help="N > 1: also time the centralised-policy mode (one in-place all-gather of the observations per step)")
     ap.add_argument("--cpu-frames-per-core", type=int, default=150)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -121,6 +121,11 @@ int ssb_set_conv_mode(ssb_ctx* ctx, int mode);
  * caller's stream, so kernel tails and memory- vs compute-bound kernels of different sub-batches overlap */
 int ssb_set_streams(ssb_ctx* ctx, int n);
 
+/* Each internal stream works through n sub-batches one after the other (default 1): sub-batches = streams x n,
+ * at least 16 envs each.  Smaller sub-batches keep the per-step intermediates (partition spectra, partition sums,
+ * waveform: 1.3 MB per env at 44.1 kHz / 16384 taps) inside the L2. */
+int ssb_set_chunks(ssb_ctx* ctx, int n);
+
 /* Profiling only: ablation switches (1 skip the spectrum MAC, 2 skip the inverse FFT, 4 skip the
  * waveform loads of the spectrogram kernel, 8 skip its FFT, 32 force the direct-form SH decode).  Results are wrong when non-zero. */
 int ssb_set_debug(ssb_ctx* ctx, int flags);

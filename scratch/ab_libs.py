@@ -27,6 +27,28 @@ def child():
                for k in range(NB)]
     out = torch.empty((B,) + r.spec_shape, device="cuda")
     res = {}
+    cfgs = os.environ.get("AB_CONFIGS")
+    if cfgs:                                   # "2x1,2x2,3x2": streams x chunks-per-stream
+        out_s = []
+        for c in cfgs.split(","):
+            st, ch = (int(v) for v in c.split("x"))
+            r.set_streams(st); r.set_chunks(ch)
+            for i in range(30):
+                r.execute(batches[i % NB], out=out)
+            torch.cuda.synchronize()
+            ts = []
+            for rep in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(200):
+                    r.execute(batches[i % NB], out=out)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) / 200)
+            out_s.append("%s=%.4f" % (c, sorted(ts)[2]))
+        print("AB %-24s ms/step %s | chk=%.6f" % (os.path.basename(os.environ.get("SSB200_LIB", "default")), " ".join(out_s),
+                                                  float(out.double().sum())), flush=True)
+        return
     for streams in (2, 1, 3, 4):
         r.set_streams(streams)
         for i in range(30):

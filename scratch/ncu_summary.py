@@ -1,0 +1,49 @@
+"""Summarise an `ncu --set full` report as one CSV (metric rows x kernel columns), the form kept under profiles/.
+
+    python scratch/ncu_summary.py profiles/prof_X.ncu-rep > profiles/prof_X_summary.csv
+"""
+import csv, io, subprocess, sys
+
+METRICS = [
+    "Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "smsp__average_warp_latency_per_inst_issued.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+]
+
+
+def main(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    seen, keep = set(), []
+    for r in data:                       # first captured launch of every kernel
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").strip()
+        if name not in seen:
+            seen.add(name)
+            keep.append(r)
+    data = keep
+    short = [r[idx["Kernel Name"]].split("(")[0].replace("void ", "").strip() for r in data]
+    w = csv.writer(sys.stdout)
+    w.writerow(["metric", "unit"] + short)
+    for m in METRICS:
+        if m not in idx:
+            continue
+        w.writerow([m, units[idx[m]]] + [r[idx[m]] for r in data])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -13,4 +13,6 @@ batch = r.prepare([AudioRequest(rir=ids[i], source=sid) for i in range(B)])
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 r.lib.ssb_set_debug(r.ctx.handle, flags)
 for i in range(4): r.execute(batch)
+spec, wave = r.execute(batch, want_wave=True)
+r.logmel(wave[:64])                      # the log-mel extension kernel, same 64-env launch size as the others
 torch.cuda.synchronize()

@@ -45,6 +45,7 @@ EXPORTS = {
     "ssb_launch_count": (C.c_int64, [C.c_void_p]),
     "ssb_set_conv_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "ssb_set_streams": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssb_set_chunks": (C.c_int, [C.c_void_p, C.c_int]),
     "ssb_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "ssb_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ssb_get_kernel_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -25,6 +25,16 @@ using namespace ssb;
 // Device-side ablation switches (ssb_set_debug bits 1, 2, 4, 8: skip the partition sums / inverse FFT / sample
 // loads / STFT) cost branches and a register in the hot kernels, so they only exist in -DSSB_ABLATION builds
 // (scratch/ablate.py); in the product build the kernels see a constant 0.
+// Read-once operands (the RIR taps, H in the partition sums, Y in the inverse FFT) can be loaded with the
+// evict-first policy (ld.global.cs) so they do not push the re-read data (source spectra, waveform) out of L2.
+#ifndef SSB_STREAM_HINTS
+#define SSB_STREAM_HINTS 1
+#endif
+#if SSB_STREAM_HINTS
+#define LD_ONCE(p) __ldcs(p)
+#else
+#define LD_ONCE(p) (*(p))
+#endif
 #ifdef SSB_ABLATION
 #define SSB_DBG(x) (x)
 #else
@@ -60,6 +70,7 @@ struct ssb_ctx {
     size_t yscratch_elems;
     int conv_mode;       // 0: mac_bins + ifft (default), 1: fused mac_ifft
     int n_streams;       // internal compute streams of ssb_render_batch (1 = caller's stream only)
+    int n_chunks;        // sub-batches each internal stream works through in turn (L2 footprint, ssb_set_chunks)
     cudaStream_t s_comp[SSB_MAX_STREAMS];
     cudaEvent_t ev_comp[SSB_MAX_STREAMS], ev_fork;
     int debug;           // ablation switches for profiling (ssb_set_debug); 0 in production
@@ -142,7 +153,7 @@ fwd_rir_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ rir_
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         int n = p * PART + t + q * P::T;
-        v[q] = n < taps ? __ldg(src + n) : make_float2(0.f, 0.f);
+        v[q] = n < taps ? (SSB_STREAM_HINTS ? __ldcs(src + n) : __ldg(src + n)) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int q = 8; q < 16; ++q) v[q] = make_float2(0.f, 0.f);
@@ -219,7 +230,7 @@ mac_bins_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
             // fast path (clip starts at offset 0): every operand is loaded exactly once, up front
             float2 h[NPMAX], x[NBMAX];
 #pragma unroll
-            for (int p = 0; p < NPMAX; ++p) h[p] = p < nparts ? hp[(long long)p * P::N] : make_float2(0.f, 0.f);
+            for (int p = 0; p < NPMAX; ++p) h[p] = p < nparts ? LD_ONCE(hp + (long long)p * P::N) : make_float2(0.f, 0.f);
 #pragma unroll
             for (int w = 0; w < NBMAX; ++w) x[w] = w < nblk ? __ldg(xp + (long long)w * P::N) : make_float2(0.f, 0.f);
 #pragma unroll
@@ -304,7 +315,7 @@ mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
         // the partition sums were formed per bin by mac_bins_kernel; H here is its output Y[env][b][N]
         const float2* __restrict__ yp = H + ((long long)env * gridDim.y + b) * P::N + t;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = (dbg & 1) ? make_float2(0.f, 0.f) : yp[i * P::T];
+        for (int i = 0; i < 16; ++i) acc[i] = (dbg & 1) ? make_float2(0.f, 0.f) : LD_ONCE(yp + i * P::T);
     } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = make_float2(0.f, 0.f);
@@ -948,6 +959,7 @@ extern "C" int ssb_create(int device, ssb_ctx** out) {
     if (prop.major < 10) SSB_FAIL(ctx, SSB_E_CUDA, "device %d is sm_%d%d; libssb200 is built for sm_100a only", device, prop.major, prop.minor);
     ctx->sm_count = prop.multiProcessorCount;
     ctx->n_streams = 2;
+    ctx->n_chunks = 1;
     {
         cudaError_t e = cudaSuccess;
         if (e == cudaSuccess) e = upload_twiddles<9>(ctx);
@@ -1013,6 +1025,12 @@ extern "C" int ssb_set_conv_mode(ssb_ctx* ctx, int mode) {
 extern "C" int ssb_set_streams(ssb_ctx* ctx, int n) {
     if (!ctx || n < 1 || n > SSB_MAX_STREAMS) return SSB_E_INVALID_ARG;
     ctx->n_streams = n;
+    return SSB_OK;
+}
+
+extern "C" int ssb_set_chunks(ssb_ctx* ctx, int n) {
+    if (!ctx || n < 1 || n > 16) return SSB_E_INVALID_ARG;
+    ctx->n_chunks = n;
     return SSB_OK;
 }
 
@@ -1265,12 +1283,17 @@ extern "C" int ssb_render_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const
     SSB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     const size_t spec_row = (size_t)SSB_SPEC_ROWS * ssb_spec_cols(plan->sr) * 2;
     const size_t y_env = (size_t)plan->n_blocks * ((size_t)1 << plan->log2n);
-    const int per = (B + S - 1) / S;
+    // S streams x C chunks: sub-batch i runs on stream i % S, so a stream works through its chunks one after the
+    // other and only S sub-batches' intermediates (H, Y, waveform: 1.3 MB per env at config 2) are live in L2 at a time
+    int C = ctx->n_chunks;
+    while (C > 1 && B / (S * C) < 16) --C;            // sub-batches of at least 16 envs
+    const int n_sub = S * C;
+    const int per = (B + n_sub - 1) / n_sub;
+    for (int i = 0; i < S; ++i) SSB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comp[i], ctx->ev_fork, 0));
     int i = 0;
     for (int e0 = 0; e0 < B; e0 += per, ++i) {
         const int nb = (B - e0 < per) ? (B - e0) : per;
-        cudaStream_t si = ctx->s_comp[i];
-        SSB_CUDA(ctx, cudaStreamWaitEvent(si, ctx->ev_fork, 0));
+        cudaStream_t si = ctx->s_comp[i % S];
         SSB_CUDA(ctx, launch_conv_any(ctx, plan, nb, d_reqs + e0, d_rir_bank, d_xpool,
                                       (float2*)d_hscratch + (size_t)e0 * plan->h_elems_per_env,
                                       ctx->yscratch ? ctx->yscratch + (size_t)e0 * y_env : nullptr,
@@ -1278,8 +1301,10 @@ extern "C" int ssb_render_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const
         rc = spectrogram_checked(ctx, nb, d_wave + (size_t)e0 * 2 * wave_stride, wave_stride, plan->sr, pad_mode,
                                  d_spec + (size_t)e0 * spec_row, si);
         if (rc) return rc;
-        SSB_CUDA(ctx, cudaEventRecord(ctx->ev_comp[i], si));
-        SSB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_comp[i], 0));
+    }
+    for (int k = 0; k < S; ++k) {
+        SSB_CUDA(ctx, cudaEventRecord(ctx->ev_comp[k], ctx->s_comp[k]));
+        SSB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_comp[k], 0));
     }
     return SSB_OK;
 }

@@ -111,6 +111,10 @@ class BatchedAudioRenderer:
         """Run render() as n sub-batches on n internal streams (overlaps kernel tails)."""
         self.ctx.check(self.lib.ssb_set_streams(self.ctx.handle, int(n)), "ssb_set_streams")
 
+    def set_chunks(self, n: int):
+        """Each internal stream works through n sub-batches in turn (smaller L2 footprint per sub-batch)."""
+        self.ctx.check(self.lib.ssb_set_chunks(self.ctx.handle, int(n)), "ssb_set_chunks")
+
     # ------------------------------------------------------------------ banks
     def add_rirs(self, rirs: Sequence) -> list:
         """Append RIRs ((L, 2) float32 arrays / tensors; None or empty => zero-RIR fallback)."""
