@@ -26,6 +26,14 @@ r.set_streams(2)
 sid = r.add_source(make_source(3, 16000))
 ids = r.add_rirs([make_rir(i, 3000) for i in range(64)])
 r.render([AudioRequest(rir=i, source=sid) for i in ids])
+r.set_chunks(2)
+spec, wave = r.render([AudioRequest(rir=i, source=sid, silent=(i % 9 == 0)) for i in ids], want_wave=True)   # 2 streams x 2 chunks
+r.set_chunks(1)
+for pm in ("reflect", "constant"):                                       # log-mel extension kernel, both pad modes / powers
+    rm = BatchedAudioRenderer(16000, 1024, pad_mode=pm)
+    for n_mels, power in ((64, 2), (13, 1), (1, 2)):
+        rm.logmel(wave[:5].clone(), n_mels=n_mels, power=power)
+torch.cuda.synchronize()
 hs = r.make_host_session(8, 3000, want_wave=True, n_chunks=2)
 hs.h_rir.numpy()[:] = np.stack([make_rir(i, 3000) for i in range(8)]); hs.set_requests(sid); hs.run(); hs.run()
 torch.cuda.synchronize()
