@@ -46,8 +46,8 @@ N_BANKS = 16            # RIR banks rotated between steps: 16 x 16.8 MB = 268 MB
 # bytes = 8*L_eff + 4*S/B_share + 8*65*T'  (spectrogram-only output)
 ALG_BYTES_PER_FRAME = 8 * TAPS + 4 * SR // ENVS_PER_GPU + 8 * 65 * 69
 # dram__bytes_read.sum + dram__bytes_write.sum per 64-env launch from the committed capture
-# profiles/prof_r01c_f32x2.ncu-rep (ncu --set full, cold-cache replay), by kernel
-NCU_DRAM_BYTES_PER_LAUNCH = {"fwd_rir_kernel": 8.16e6, "mac_bins_kernel": 17.58e6, "mac_ifft_kernel": 45.26e6,
+# profiles/prof_r01d.ncu-rep (ncu --set full, cold-cache replay), by kernel
+NCU_DRAM_BYTES_PER_LAUNCH = {"fwd_rir_kernel": 8.42e6, "mac_bins_kernel": 17.79e6, "mac_ifft_kernel": 46.86e6,
                              "spectrogram_kernel": 22.62e6}
 ALG_FLOP_PER_FRAME = 17.3e6   # 2 packed 65536-pt FFT equivalents + mul + 276 packed 512-pt FFTs
 FP32_PEAK_TFLOPS = 75.0       # nominal B200 FP32 SIMT, SURVEY.md 8(d)
@@ -388,7 +388,7 @@ def run_gpu(args, rank, local_rank, world):
                 "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom, 0.0) * launches_per_step[dom] if args.log2n in (0, 12) else None,
-                "traffic_source": "profiles/prof_r01c_f32x2.ncu-rep: dram__bytes_read.sum + dram__bytes_write.sum of the "
+                "traffic_source": "profiles/prof_r01d.ncu-rep: dram__bytes_read.sum + dram__bytes_write.sum of the "
                                   "dominant kernel (cold-cache replay, 64-env launch) x its launches per step",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_step": alg_bytes_launch, "kernel_ms": dom_ms,

@@ -213,6 +213,14 @@ def test_full_size_c2_properties():
         spec3, wave3 = r.render(reqs, want_wave=True)
         torch.cuda.synchronize()
         assert np.array_equal(wave3.cpu().numpy(), wave_h) and np.array_equal(spec3.cpu().numpy(), spec_h)
+    # streams x chunks (each stream works through several smaller sub-batches in turn): bit-identical too
+    for streams, chunks in ((2, 2), (2, 4), (3, 2), (4, 16)):
+        r.set_streams(streams)
+        r.set_chunks(chunks)
+        spec4, wave4 = r.render(reqs, want_wave=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(wave4.cpu().numpy(), wave_h) and np.array_equal(spec4.cpu().numpy(), spec_h)
+    r.set_chunks(1)
     r.set_streams(1)
 
 
