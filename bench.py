@@ -49,6 +49,12 @@ ALG_BYTES_PER_FRAME = 8 * TAPS + 4 * SR // ENVS_PER_GPU + 8 * 65 * 69
 # profiles/prof_r01d.ncu-rep (ncu --set full, cold-cache replay), by kernel
 NCU_DRAM_BYTES_PER_LAUNCH = {"fwd_rir_kernel": 8.42e6, "mac_bins_kernel": 17.79e6, "mac_ifft_kernel": 46.86e6,
                              "spectrogram_kernel": 22.62e6}
+# same capture: FMA-pipe busy cycles per SM (sm__pipe_fma_cycles_active.avg) and executed warp-instructions
+# (smsp__inst_executed.sum) of one 64-env launch of each kernel -- the compute roofline this FP32 path really has
+NCU_FMA_PIPE_CYCLES_PER_LAUNCH = {"fwd_rir_kernel": 4663.0, "mac_bins_kernel": 8912.0, "mac_ifft_kernel": 13389.0,
+                                  "spectrogram_kernel": 21105.0}
+NCU_WARP_INST_PER_LAUNCH = {"fwd_rir_kernel": 2.359e6, "mac_bins_kernel": 5.456e6, "mac_ifft_kernel": 8.000e6,
+                            "spectrogram_kernel": 11.864e6}
 ALG_FLOP_PER_FRAME = 17.3e6   # 2 packed 65536-pt FFT equivalents + mul + 276 packed 512-pt FFTs
 FP32_PEAK_TFLOPS = 75.0       # nominal B200 FP32 SIMT, SURVEY.md 8(d)
 
@@ -380,6 +386,8 @@ def run_gpu(args, rank, local_rank, world):
         achieved = alg_bytes_launch / (dom_ms * 1e-3) / 1e9
         step_ms = ms_max / args.steps
         kernel_sum = sum(per_step_ms.values())
+        sm_mhz = (clocks.get("sm_mhz") or 1965.0)
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -399,7 +407,15 @@ def run_gpu(args, rank, local_rank, world):
                 "path_achieved_gbs": alg_bytes_launch / (step_ms * 1e-3) / 1e9,
                 "path_frac_hbm": alg_bytes_launch / (step_ms * 1e-3) / 1e9 / peak,
                 "fp32_frac": (value / world) * ALG_FLOP_PER_FRAME / (FP32_PEAK_TFLOPS * 1e12),
-                "note": "FFT work is FP32-FMA bound (about 100 flop/B at algorithmic traffic); see DESIGN.md",
+                # compute roofline of the kernels as built (default plan only): time the FMA pipes / the issue slots
+                # would need for one step's instructions (counts from profiles/prof_r01d.ncu-rep) over the step time
+                "fma_pipe_frac": (sum(NCU_FMA_PIPE_CYCLES_PER_LAUNCH[k] * launches_per_step[k] for k in hot)
+                                  / (sm_mhz * 1e6) / (step_ms * 1e-3)) if args.log2n in (0, 12) and args.conv_mode == 0 else None,
+                "issue_slot_frac": (sum(NCU_WARP_INST_PER_LAUNCH[k] * launches_per_step[k] for k in hot)
+                                    / (sm_count * 4) / (sm_mhz * 1e6) / (step_ms * 1e-3)) if args.log2n in (0, 12) and args.conv_mode == 0 else None,
+                "note": "FFT work is FP32-pipe bound (about 100 flop/B at algorithmic traffic): fma_pipe_frac / issue_slot_frac are the "
+                        "fractions that measure kernel quality; the launch sizes of the capture are 64-env sub-batches, the same "
+                        "as the 2 launches per kernel per step here; see DESIGN.md",
             },
             "e2e": {"value": B * world * e2e_steps / (e2e_ms_max * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes,
