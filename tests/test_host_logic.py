@@ -148,3 +148,122 @@ def test_shard_envs_partition():
     for world in (1, 2, 4, 8):
         parts = [shard_envs(13, r, world) for r in range(world)]
         assert sorted(sum(parts, [])) == list(range(13))
+
+
+# ---------------------------------------------------------------------------------- request preparation
+def _host_only_renderer(n_terms=2):
+    """A BatchedAudioRenderer with the device parts stubbed out: exercises the host-side request arithmetic
+    of prepare() (bank offsets, effective taps, window-set lookups) without CUDA."""
+    import torch
+    from soundspaces_b200._lib import Plan
+    from soundspaces_b200.renderer import BatchedAudioRenderer
+    from soundspaces_b200.planning import window_layout
+    r = object.__new__(BatchedAudioRenderer)
+    r.sr, r.P, r.N, r.max_taps = 16000, 2048, 4096, 20000
+    plan = Plan()
+    plan.log2n, plan.block, plan.sr, plan.n_blocks, plan.max_parts, plan.n_terms = 12, 2048, 16000, 8, 10, n_terms
+    plan.h_elems_per_env = n_terms * 10 * 4096
+    r.plan = plan
+    r.device = torch.device("cpu")
+    r._bank_index = None
+    r._rir_len = [100, 4097, 0, 20000, 9000, 16000]
+    r._rir_off = [0, 100, 0, 4197, 24197, 33197]
+    calls = []
+
+    def windows(source, offset, wrap, out_samples):            # deterministic stand-in for the cached spectra
+        calls.append((source, offset, wrap, out_samples))
+        nblk, wofs, nw = window_layout(r.P, plan.max_parts, offset, out_samples)
+        return (1000 * source + offset + 7 * int(wrap) + out_samples, nw, wofs)
+    r._windows = windows
+    return r, calls
+
+
+def _prepare_reference(r, requests):
+    """The per-request loop the vectorised _prepare replaced (same field semantics)."""
+    from soundspaces_b200._lib import REQ_DTYPE, SSB_FLAG_SILENT
+    from soundspaces_b200.planning import effective_taps
+    reqs = np.zeros(len(requests), dtype=REQ_DTYPE)
+
+    def fill(term, rir_id, source, offset, wrap, out_samples):
+        if rir_id is None or rir_id < 0 or r._rir_len[rir_id] == 0:
+            return
+        x_off, nw, wofs = r._windows(source, offset, wrap, out_samples)
+        term["rir_offset"], term["x_offset"] = r._rir_off[rir_id], x_off
+        term["rir_taps"] = effective_taps(r._rir_len[rir_id], offset, out_samples)
+        term["x_nw"], term["x_wofs"] = nw, wofs
+    for i, q in enumerate(requests):
+        outs = r.sr if q.out_samples is None else int(q.out_samples)
+        reqs[i]["out_samples"] = outs
+        if q.silent:
+            reqs[i]["flags"] = SSB_FLAG_SILENT
+            continue
+        fill(reqs[i]["term"][0], q.rir, q.source, int(q.offset), q.wrap, outs)
+        if q.distractor_source is not None:
+            fill(reqs[i]["term"][1], q.distractor_rir, q.distractor_source, 0, False, outs)
+    return reqs
+
+
+def test_prepare_vectorised_matches_per_request_loop():
+    from soundspaces_b200 import AudioRequest
+    rng = np.random.default_rng(3)
+    r, calls = _host_only_renderer()
+    reqs = []
+    for i in range(200):
+        reqs.append(AudioRequest(
+            rir=[0, 1, 2, 3, 4, 5, -1, None][rng.integers(8)], source=int(rng.integers(3)),
+            offset=int(rng.choice([0, 0, 0, 16000, 32000, 8000, 12345])),
+            out_samples=[None, None, 4000, 16000, 1][rng.integers(5)], wrap=bool(rng.integers(2)),
+            silent=bool(rng.random() < 0.1),
+            distractor_rir=[None, 1, 2, 4][rng.integers(4)], distractor_source=[None, None, 0, 2][rng.integers(4)]))
+    got = r._prepare(reqs)
+    n_vec = len(calls)
+    del calls[:]
+    ref = _prepare_reference(r, reqs)
+    assert got.n == 200 and got.reqs_host.dtype == ref.dtype
+    assert got.reqs_host.tobytes() == ref.tobytes()                       # identical, byte for byte
+    assert bytes(got.reqs_dev.numpy()) == ref.tobytes()
+    assert n_vec <= 2 * len(set(calls)) and n_vec < len(calls)            # one lookup per distinct window set and term
+    # empty batch, all-silent batch
+    assert r._prepare([]).n == 0
+    z = r._prepare([AudioRequest(rir=0, source=0, silent=True)] * 3).reqs_host
+    assert (z["flags"] == 1).all() and not z["term"]["rir_taps"].any()
+
+
+def test_prepare_errors_like_before():
+    from soundspaces_b200 import AudioRequest
+    r, _ = _host_only_renderer(n_terms=1)
+    with pytest.raises(ValueError, match="unknown RIR id"):
+        r._prepare([AudioRequest(rir=0, source=0), AudioRequest(rir=6, source=0)])
+    with pytest.raises(ValueError, match="out_samples"):
+        r._prepare([AudioRequest(rir=0, source=0, out_samples=0)])
+    with pytest.raises(ValueError, match="out_samples"):
+        r._prepare([AudioRequest(rir=0, source=0, out_samples=16001)])
+    with pytest.raises(ValueError, match="n_terms=1"):
+        r._prepare([AudioRequest(rir=0, source=0, distractor_rir=1, distractor_source=0)])
+    r.plan.max_parts = 4                                                  # 8192 taps: RIR 3 (20000, cut to 16000) no longer fits
+    with pytest.raises(ValueError, match="RIR 3 needs 16000 taps"):
+        r._prepare([AudioRequest(rir=1, source=0), AudioRequest(rir=3, source=0)])
+    # the bank index follows the bank
+    r.plan.max_parts = 10
+    a = r._prepare([AudioRequest(rir=4, source=0)]).reqs_host["term"][0, 0]
+    assert a["rir_offset"] == 24197 and a["rir_taps"] == 9000
+    r._rir_off[4], r._rir_len[4] = 5, 50
+    r._bank_index = None                                                  # what every bank mutation does
+    a = r._prepare([AudioRequest(rir=4, source=0)]).reqs_host["term"][0, 0]
+    assert a["rir_offset"] == 5 and a["rir_taps"] == 50
+
+
+def test_prepare_arrays_equals_prepare():
+    from soundspaces_b200 import AudioRequest
+    r, _ = _host_only_renderer()
+    rir = np.array([0, 1, -1, 3, 4, 5, 2, 1])
+    off = np.array([0, 16000, 0, 0, 8000, 0, 0, 32000])
+    sil = np.array([0, 0, 0, 1, 0, 0, 0, 0], dtype=bool)
+    drir = np.array([-1, 4, -1, -1, -1, 1, -1, -1])
+    dsrc = np.array([-1, 2, -1, -1, -1, 0, -1, -1])
+    a = r.prepare_arrays(rir, 1, offset=off, silent=sil, distractor_rir=drir, distractor_source=dsrc)
+    b = r.prepare([AudioRequest(rir=int(rir[i]), source=1, offset=int(off[i]), silent=bool(sil[i]),
+                                distractor_rir=None if drir[i] < 0 else int(drir[i]),
+                                distractor_source=None if dsrc[i] < 0 else int(dsrc[i])) for i in range(8)])
+    assert a.n == 8 and a.reqs_host.tobytes() == b.reqs_host.tobytes()
+    assert r.prepare_arrays(np.arange(3), 0, out_samples=4000).reqs_host["out_samples"].tolist() == [4000] * 3
