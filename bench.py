@@ -386,8 +386,19 @@ def run_gpu(args, rank, local_rank, world):
         achieved = alg_bytes_launch / (dom_ms * 1e-3) / 1e9
         step_ms = ms_max / args.steps
         kernel_sum = sum(per_step_ms.values())
-        sm_mhz = (clocks.get("sm_mhz") or 1965.0)
-        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        # compute roofline of the kernels as built (default plan only): the time the FMA pipes / the issue slots need
+        # for one step's instructions (counts from profiles/prof_r01d.ncu-rep) over the measured step time
+        fma_frac = issue_frac = None
+        try:
+            if args.log2n in (0, 12) and args.conv_mode == 0:
+                sm_mhz = (clocks.get("sm_mhz") or 1965.0)
+                sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+                fma_frac = (sum(NCU_FMA_PIPE_CYCLES_PER_LAUNCH[k] * launches_per_step[k] for k in hot)
+                            / (sm_mhz * 1e6) / (step_ms * 1e-3))
+                issue_frac = (sum(NCU_WARP_INST_PER_LAUNCH[k] * launches_per_step[k] for k in hot)
+                              / (sm_count * 4) / (sm_mhz * 1e6) / (step_ms * 1e-3))
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -407,12 +418,7 @@ def run_gpu(args, rank, local_rank, world):
                 "path_achieved_gbs": alg_bytes_launch / (step_ms * 1e-3) / 1e9,
                 "path_frac_hbm": alg_bytes_launch / (step_ms * 1e-3) / 1e9 / peak,
                 "fp32_frac": (value / world) * ALG_FLOP_PER_FRAME / (FP32_PEAK_TFLOPS * 1e12),
-                # compute roofline of the kernels as built (default plan only): time the FMA pipes / the issue slots
-                # would need for one step's instructions (counts from profiles/prof_r01d.ncu-rep) over the step time
-                "fma_pipe_frac": (sum(NCU_FMA_PIPE_CYCLES_PER_LAUNCH[k] * launches_per_step[k] for k in hot)
-                                  / (sm_mhz * 1e6) / (step_ms * 1e-3)) if args.log2n in (0, 12) and args.conv_mode == 0 else None,
-                "issue_slot_frac": (sum(NCU_WARP_INST_PER_LAUNCH[k] * launches_per_step[k] for k in hot)
-                                    / (sm_count * 4) / (sm_mhz * 1e6) / (step_ms * 1e-3)) if args.log2n in (0, 12) and args.conv_mode == 0 else None,
+                "fma_pipe_frac": fma_frac, "issue_slot_frac": issue_frac,
                 "note": "FFT work is FP32-pipe bound (about 100 flop/B at algorithmic traffic): fma_pipe_frac / issue_slot_frac are the "
                         "fractions that measure kernel quality; the launch sizes of the capture are 64-env sub-batches, the same "
                         "as the 2 launches per kernel per step here; see DESIGN.md",
