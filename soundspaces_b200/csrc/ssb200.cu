@@ -201,6 +201,9 @@ fwd_src_kernel(const float* __restrict__ src, int S, long long m0, int wrap, int
 // partition for every block: 4.9 MB per env at config 2 against 0.26 + 0.70 MB here); repeated
 // touches of the same slot column are L1 hits.  grid (N / 256, B); block 256.
 // ---------------------------------------------------------------------------
+#ifndef MACB_PREFETCH
+#define MACB_PREFETCH 0          // 0: all source windows loaded up front (measured default)
+#endif
 #ifdef MACB_MIN_BLOCKS
 #define MACB_BOUNDS __launch_bounds__(256, MACB_MIN_BLOCKS)
 #else
@@ -231,10 +234,21 @@ mac_bins_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
             float2 h[NPMAX], x[NBMAX];
 #pragma unroll
             for (int p = 0; p < NPMAX; ++p) h[p] = p < nparts ? LD_ONCE(hp + (long long)p * P::N) : make_float2(0.f, 0.f);
+#if MACB_PREFETCH > 0
+            // UNMEASURED round-2 candidate: source windows fetched MACB_PREFETCH blocks ahead of their first use
+            // instead of all up front, so only 8 + MACB_PREFETCH of them are live (fewer registers, one more CTA per SM)
+#pragma unroll
+            for (int w = 0; w < MACB_PREFETCH; ++w) x[w] = w < nblk ? __ldg(xp + (long long)w * P::N) : make_float2(0.f, 0.f);
+#else
 #pragma unroll
             for (int w = 0; w < NBMAX; ++w) x[w] = w < nblk ? __ldg(xp + (long long)w * P::N) : make_float2(0.f, 0.f);
+#endif
 #pragma unroll
             for (int b = 0; b < NBMAX; ++b) {
+#if MACB_PREFETCH > 0
+                if (b + MACB_PREFETCH < NBMAX)
+                    x[b + MACB_PREFETCH] = b + MACB_PREFETCH < nblk ? __ldg(xp + (long long)(b + MACB_PREFETCH) * P::N) : make_float2(0.f, 0.f);
+#endif
                 if (b < nblk) {
                     // x * h = x.x * h + i * (x.y * h): two accumulators, ONE swizzled add at the end, so the
                     // inner loop is two FFMA2 per complex multiply-accumulate with no operand shuffling
