@@ -13,11 +13,13 @@ build)
     nvcc $FL -DMACB_PREFETCH=4 -o scratch/ab/lib_pf4.so $SRC &
     nvcc $FL -DMACB_PREFETCH=6 -o scratch/ab/lib_pf6.so $SRC &
     nvcc $FL -DMACB_PREFETCH=4 -DMACB_MIN_BLOCKS=4 -o scratch/ab/lib_pf4_mc4.so $SRC &
+    nvcc $FL -DIFFT_TW_GLOBAL=1 -o scratch/ab/lib_twg.so $SRC &
+    nvcc $FL -DIFFT_TW_GLOBAL=1 -DMACB_PREFETCH=4 -o scratch/ab/lib_twg_pf4.so $SRC &
     wait; ls -la scratch/ab ;;
 run)
     mkdir -p gpurun_out
     python scratch/ab_libs.py scratch/ab/lib_base.so scratch/ab/lib_pf3.so scratch/ab/lib_pf4.so scratch/ab/lib_pf6.so \
-        scratch/ab/lib_pf4_mc4.so scratch/ab/lib_base.so 2>&1 | grep -E "^AB|rror" | tee gpurun_out/ab_r02_macb_prefetch.log
+        scratch/ab/lib_pf4_mc4.so scratch/ab/lib_twg.so scratch/ab/lib_twg_pf4.so scratch/ab/lib_base.so 2>&1 | grep -E "^AB|rror" | tee gpurun_out/ab_r02_prepared.log
     # parity of the winner: SSB200_LIB=$PWD/scratch/ab/lib_pf4.so python -m pytest tests/test_gpu_parity.py -q -m gpu
     ;;
 *) echo "usage: $0 build|run" ;;

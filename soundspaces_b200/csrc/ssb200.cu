@@ -288,6 +288,9 @@ mac_bins_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
 // multiply-accumulate over partitions + inverse FFT + emit
 // grid (B, n_blocks); block T.
 // ---------------------------------------------------------------------------
+#ifndef IFFT_TW_GLOBAL
+#define IFFT_TW_GLOBAL 0         // 0: twiddles of passes >= 1 staged in shared memory (measured default)
+#endif
 #ifndef IFFT12_MIN_BLOCKS
 #define IFFT12_MIN_BLOCKS 5      // resident CTAs per SM asked of ptxas for the N = 4096 instance
 #endif
@@ -353,9 +356,15 @@ mac_ifft_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
         }
     }
     }
+#if IFFT_TW_GLOBAL
+    // UNMEASURED round-2 candidate: read the later passes' twiddles straight from the (L1-resident) global table, as the
+    // STFT kernel does, instead of staging them in shared memory behind a block barrier
+    if (!(dbg & 2)) fft_inverse<LOG2N>(acc, t, smem, tw, tw + P::TW_SMALL_OFFSET);
+#else
     stage_small_twiddles<LOG2N>(stw, tw, t);
     __syncthreads();
     if (!(dbg & 2)) fft_inverse<LOG2N>(acc, t, smem, tw, stw);
+#endif
     constexpr float scale = 1.0f / (float)P::N;
 #pragma unroll
     for (int q = 8; q < 16; ++q) {
