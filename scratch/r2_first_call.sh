@@ -15,11 +15,13 @@ build)
     nvcc $FL -DMACB_PREFETCH=4 -DMACB_MIN_BLOCKS=4 -o scratch/ab/lib_pf4_mc4.so $SRC &
     nvcc $FL -DIFFT_TW_GLOBAL=1 -o scratch/ab/lib_twg.so $SRC &
     nvcc $FL -DIFFT_TW_GLOBAL=1 -DMACB_PREFETCH=4 -o scratch/ab/lib_twg_pf4.so $SRC &
-    wait; ls -la scratch/ab ;;
+    nvcc $FL -o scratch/libfft64_probe.so scratch/fft64_probe.cu &
+    wait; ls -la scratch/ab scratch/libfft64_probe.so ;;
 run)
     mkdir -p gpurun_out
     python scratch/ab_libs.py scratch/ab/lib_base.so scratch/ab/lib_pf3.so scratch/ab/lib_pf4.so scratch/ab/lib_pf6.so \
         scratch/ab/lib_pf4_mc4.so scratch/ab/lib_twg.so scratch/ab/lib_twg_pf4.so scratch/ab/lib_base.so 2>&1 | grep -E "^AB|rror" | tee gpurun_out/ab_r02_prepared.log
+    python scratch/fft64_probe.py 2>&1 | tee gpurun_out/fft64_probe_r02.log
     # parity of the winner: SSB200_LIB=$PWD/scratch/ab/lib_pf4.so python -m pytest tests/test_gpu_parity.py -q -m gpu
     ;;
 *) echo "usage: $0 build|run" ;;
