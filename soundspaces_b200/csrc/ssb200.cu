@@ -74,6 +74,7 @@ struct ssb_ctx {
     cudaStream_t s_comp[SSB_MAX_STREAMS];
     cudaEvent_t ev_comp[SSB_MAX_STREAMS], ev_fork;
     int debug;           // ablation switches for profiling (ssb_set_debug); 0 in production
+    bool attr_sh, attr_shf;   // cudaFuncSetAttribute is per DEVICE: opt-in flags live in the (per-device) context
     // mel filterbanks by (sr, n_mels), built on first use (ssb_logmel_batch)
     struct MelBank { int sr, n_mels; int2* rows; int* ofs; float* w; };
     std::vector<MelBank>* mel;
@@ -96,6 +97,35 @@ struct ssb_ctx {
     } while (0)
 
 static const int kSupportedLog2[] = {9, 12, 13, 14};
+
+// Every ABI entry runs on the context's device, whatever the caller's current device is, and restores the
+// caller's device afterwards (one process may hold contexts on several devices: per-rank trainers do not, but
+// the reference's ``GPU_DEVICE_ID`` / ``TORCH_GPU_ID`` split can put the policy on another device than the renderer).
+struct DevGuard {
+    int prev = -1, dev;
+    explicit DevGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+
+// No C++ exception may cross the C ABI (include/ssb200.h: "never throws"): allocating STL containers in an entry
+// are wrapped here and reported as SSB_E_OOM / SSB_E_CUDA with a message.
+template <class F>
+static int abi_call(ssb_ctx* ctx, F&& body) noexcept {
+    if (!ctx) return SSB_E_INVALID_ARG;
+    try {
+        DevGuard g(ctx->device);
+        return body();
+    } catch (const std::bad_alloc&) {
+        snprintf(ctx->err, sizeof(ctx->err), "out of host memory");
+        return SSB_E_OOM;
+    } catch (...) {
+        snprintf(ctx->err, sizeof(ctx->err), "unexpected C++ exception inside libssb200");
+        return SSB_E_CUDA;
+    }
+}
 
 struct LaunchTimer {          // records an event pair around one kernel launch when timing is on
     ssb_ctx* ctx; cudaStream_t st; TimedLaunch tl; bool on;
@@ -966,6 +996,8 @@ static cudaError_t upload_twiddles(ssb_ctx* ctx) {
 
 extern "C" int ssb_version(void) { return 100; }
 
+static int create_impl(ssb_ctx* ctx, int device);
+
 extern "C" int ssb_create(int device, ssb_ctx** out) {
     if (!out) return SSB_E_INVALID_ARG;
     *out = nullptr;
@@ -976,7 +1008,16 @@ extern "C" int ssb_create(int device, ssb_ctx** out) {
     ctx->timed = new (std::nothrow) std::vector<TimedLaunch>();
     ctx->mel = new (std::nothrow) std::vector<ssb_ctx::MelBank>();
     *out = ctx;   // returned even on failure so that ssb_last_error works; caller destroys
-    SSB_CUDA(ctx, cudaSetDevice(device));
+    if (!ctx->timed || !ctx->mel) SSB_FAIL(ctx, SSB_E_OOM, "out of host memory");
+    return abi_call(ctx, [&] { return create_impl(ctx, device); });   // the caller's current device is restored
+}
+
+static int create_impl(ssb_ctx* ctx, int device) {
+    {   // abi_call's guard has already selected the device; surface a bad ordinal as an error
+        int cur = -1;
+        SSB_CUDA(ctx, cudaGetDevice(&cur));
+        if (cur != device) SSB_CUDA(ctx, cudaSetDevice(device));
+    }
     cudaDeviceProp prop;
     SSB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) SSB_FAIL(ctx, SSB_E_CUDA, "device %d is sm_%d%d; libssb200 is built for sm_100a only", device, prop.major, prop.minor);
@@ -1008,6 +1049,7 @@ extern "C" int ssb_create(int device, ssb_ctx** out) {
 
 extern "C" void ssb_destroy(ssb_ctx* ctx) {
     if (!ctx) return;
+    DevGuard guard(ctx->device);
     for (int l = 0; l < 16; ++l)
         if (ctx->tw[l]) cudaFree(ctx->tw[l]);
     if (ctx->window) cudaFree(ctx->window);
@@ -1069,7 +1111,7 @@ extern "C" int ssb_set_kernel_timing(ssb_ctx* ctx, int enable) {
     return SSB_OK;
 }
 
-extern "C" int ssb_get_kernel_timing(ssb_ctx* ctx, double* ms_sum, int64_t* counts) {
+static int ssb_get_kernel_timing_impl(ssb_ctx* ctx, double* ms_sum, int64_t* counts) {
     if (!ctx || !ms_sum || !counts || !ctx->timed) return SSB_E_INVALID_ARG;
     for (int k = 0; k < K_COUNT; ++k) { ms_sum[k] = 0.0; counts[k] = 0; }
     for (auto& tl : *ctx->timed) {
@@ -1130,7 +1172,7 @@ static cudaError_t launch_src(ssb_ctx* ctx, const float* d_src, int S, int64_t m
     return cudaGetLastError();
 }
 
-extern "C" int ssb_source_windows(ssb_ctx* ctx, const ssb_plan* plan, const float* d_src, int S, int64_t m0, int wrap,
+static int ssb_source_windows_impl(ssb_ctx* ctx, const ssb_plan* plan, const float* d_src, int S, int64_t m0, int wrap,
                                   int nw, int wofs, void* d_x, void* stream) {
     int rc = check_plan(ctx, plan);
     if (rc) return rc;
@@ -1211,7 +1253,7 @@ static cudaError_t launch_conv_any(ssb_ctx* ctx, const ssb_plan* plan, int B, co
     }
 }
 
-extern "C" int ssb_convolve_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs,
+static int ssb_convolve_batch_impl(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs,
                                   const float* d_rir_bank, const void* d_xpool, void* d_hscratch, float* d_wave,
                                   int64_t wave_stride, void* stream) {
     int rc = check_plan(ctx, plan);
@@ -1228,7 +1270,7 @@ extern "C" int ssb_convolve_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, con
     return SSB_OK;
 }
 
-extern "C" int ssb_crossfade_batch(ssb_ctx* ctx, int B, const float* d_prev, float* d_cur, int sr, int64_t wave_stride,
+static int ssb_crossfade_batch_impl(ssb_ctx* ctx, int B, const float* d_prev, float* d_cur, int sr, int64_t wave_stride,
                                    const uint8_t* d_enable, void* stream) {
     if (!ctx) return SSB_E_INVALID_ARG;
     if (B == 0) return SSB_OK;
@@ -1245,7 +1287,7 @@ extern "C" int ssb_crossfade_batch(ssb_ctx* ctx, int B, const float* d_prev, flo
 static int spectrogram_checked(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int pad_mode,
                                float* d_spec, cudaStream_t st);
 
-extern "C" int ssb_spectrogram_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int pad_mode,
+static int ssb_spectrogram_batch_impl(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int pad_mode,
                                      float* d_spec, void* stream) {
     return spectrogram_checked(ctx, B, d_wave, wave_stride, sr, pad_mode, d_spec, (cudaStream_t)stream);
 }
@@ -1279,16 +1321,16 @@ static int spectrogram_checked(ssb_ctx* ctx, int B, const float* d_wave, int64_t
 // kernel chains run on S internal streams forked from / joined to the caller's stream: the tail of one
 // kernel (partial last wave) overlaps the next sub-batch's work, and memory-bound kernels of one chain
 // overlap compute-bound kernels of another.
-extern "C" int ssb_render_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs, const float* d_rir_bank,
+static int ssb_render_batch_impl(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs, const float* d_rir_bank,
                                 const void* d_xpool, void* d_hscratch, float* d_wave, int64_t wave_stride, int pad_mode,
                                 float* d_spec, void* stream) {
-    int S = ctx ? ctx->n_streams : 1;
+    int S = ctx->n_streams;
     if (S > SSB_MAX_STREAMS) S = SSB_MAX_STREAMS;
     if (S > B / 32) S = B / 32;                       // sub-batches of at least 32 envs
     if (S <= 1) {
-        int rc = ssb_convolve_batch(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_hscratch, d_wave, wave_stride, stream);
+        int rc = ssb_convolve_batch_impl(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_hscratch, d_wave, wave_stride, stream);
         if (rc) return rc;
-        return ssb_spectrogram_batch(ctx, B, d_wave, wave_stride, plan->sr, pad_mode, d_spec, stream);
+        return ssb_spectrogram_batch_impl(ctx, B, d_wave, wave_stride, plan->sr, pad_mode, d_spec, stream);
     }
     int rc = check_plan(ctx, plan);
     if (rc) return rc;
@@ -1335,7 +1377,7 @@ extern "C" int ssb_render_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const
 // Host-buffer entry.  n_chunks > 1 pipelines the batch: chunk c+1's H2D copy (copy stream) overlaps
 // chunk c's kernels (caller's stream) and chunk c-1's D2H copy (second copy stream); PCIe is full
 // duplex, so a step costs about max(H2D, kernels, D2H) instead of their sum.
-extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* h_reqs, const float* h_rir,
+static int ssb_render_batch_host_impl(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* h_reqs, const float* h_rir,
                                      int64_t rir_bytes, float* d_rir_staging, ssb_req* d_reqs_staging, const void* d_xpool,
                                      void* d_hscratch, float* d_wave, int64_t wave_stride, int pad_mode, float* d_spec,
                                      float* h_spec, float* h_wave, int n_chunks, void* stream) {
@@ -1353,7 +1395,7 @@ extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, 
         SSB_CUDA(ctx, cudaMemcpyAsync(d_reqs_staging, h_reqs, (size_t)B * sizeof(ssb_req), cudaMemcpyHostToDevice, st));
         ctx->last_h2d_bytes = rir_bytes + (int64_t)B * (int64_t)sizeof(ssb_req);
         ctx->last_d2h_bytes = (int64_t)B * (int64_t)spec_row * 4 + (h_wave ? (int64_t)B * 2 * plan->sr * 4 : 0);
-        rc = ssb_render_batch(ctx, plan, B, d_reqs_staging, d_rir_staging, d_xpool, d_hscratch, d_wave, wave_stride,
+        rc = ssb_render_batch_impl(ctx, plan, B, d_reqs_staging, d_rir_staging, d_xpool, d_hscratch, d_wave, wave_stride,
                               pad_mode, d_spec, stream);
         if (rc) return rc;
         SSB_CUDA(ctx, cudaMemcpyAsync(h_spec, d_spec, (size_t)B * spec_row * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1413,7 +1455,7 @@ extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, 
         }
         SSB_CUDA(ctx, cudaEventRecord(ctx->ev[2 * c], ctx->s_h2d));
         SSB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[2 * c], 0));
-        rc = ssb_render_batch(ctx, plan, nb, d_reqs_staging + e0, d_rir_staging, d_xpool,
+        rc = ssb_render_batch_impl(ctx, plan, nb, d_reqs_staging + e0, d_rir_staging, d_xpool,
                               (float2*)d_hscratch + (size_t)e0 * plan->h_elems_per_env, d_wave + (size_t)e0 * 2 * wave_stride,
                               wave_stride, pad_mode, d_spec + (size_t)e0 * spec_row, stream);
         if (rc) return rc;
@@ -1439,7 +1481,7 @@ extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, 
     return SSB_OK;
 }
 
-extern "C" int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int L, const float* d_az_deg, const float* d_hbank,
+static int ssb_sh_decode_batch_impl(ssb_ctx* ctx, int B, const float* d_amb, int L, const float* d_az_deg, const float* d_hbank,
                                    void* d_filters, float* d_out_rir, void* stream) {
     if (!ctx) return SSB_E_INVALID_ARG;
     if (B == 0) return SSB_OK;
@@ -1449,10 +1491,9 @@ extern "C" int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int 
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int SPAN = SH_TILE + SH_DELAY + SH_TAPS - 1;
     const size_t smem = (size_t)(SH_CH * SPAN + 1) * sizeof(float) + (size_t)SH_CH * SH_TAPS * sizeof(float2);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_sh) {
         SSB_CUDA(ctx, cudaFuncSetAttribute(sh_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->attr_sh = true;
     }
     sh_filters_kernel<<<B, SH_TAPS, 0, st>>>(d_hbank, d_az_deg, (float2*)d_filters);
     SSB_CUDA(ctx, cudaGetLastError());
@@ -1466,11 +1507,10 @@ extern "C" int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int 
             ctx->gscratch_elems = need;
         }
         const size_t fsmem = (P::SMEM_ELEMS + P::TW_SMALL_ELEMS) * sizeof(float2);
-        static bool fattr = false;
-        if (!fattr) {
+        if (!ctx->attr_shf) {
             SSB_CUDA(ctx, cudaFuncSetAttribute(sh_filter_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
             SSB_CUDA(ctx, cudaFuncSetAttribute(sh_ols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            fattr = true;
+            ctx->attr_shf = true;
         }
         sh_filter_fft_kernel<<<dim3(SH_CH, B), P::T, fsmem, st>>>((const float2*)d_filters, ctx->gscratch, ctx->tw[SHF_LOG2N]);
         SSB_CUDA(ctx, cudaGetLastError());
@@ -1536,7 +1576,7 @@ static void build_mel_rows(int sr, int n_mels, std::vector<int2>& rows, std::vec
 extern "C" int ssb_mel_filterbank(int sr, int n_mels, float* h_out) {
     if (sr < SSB_N_FFT || n_mels < 1 || n_mels > MEL_MAX || !h_out) return SSB_E_INVALID_ARG;
     std::vector<int2> rows; std::vector<int> ofs; std::vector<float> w;
-    build_mel_rows(sr, n_mels, rows, ofs, w);
+    try { build_mel_rows(sr, n_mels, rows, ofs, w); } catch (...) { return SSB_E_OOM; }
     const int n_bins = SSB_N_FFT / 2 + 1;
     for (int j = 0; j < n_mels; ++j) {
         for (int k = 0; k < n_bins; ++k) h_out[j * n_bins + k] = 0.f;
@@ -1564,7 +1604,7 @@ static int get_mel_bank(ssb_ctx* ctx, int sr, int n_mels, const ssb_ctx::MelBank
 
 extern "C" int ssb_logmel_frames(int sr) { return 1 + sr / SSB_HOP; }
 
-extern "C" int ssb_logmel_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int n_mels, int power,
+static int ssb_logmel_batch_impl(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int n_mels, int power,
                                 int pad_mode, float* d_out, void* stream) {
     if (!ctx) return SSB_E_INVALID_ARG;
     if (B == 0) return SSB_OK;
@@ -1589,7 +1629,7 @@ extern "C" int ssb_logmel_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_
     return SSB_OK;
 }
 
-extern "C" int ssb_intensity_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int num_frame,
+static int ssb_intensity_batch_impl(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int num_frame,
                                    float* d_out, void* stream) {
     if (!ctx) return SSB_E_INVALID_ARG;
     if (B == 0) return SSB_OK;
@@ -1608,7 +1648,7 @@ extern "C" int ssb_host_copy_bytes(const ssb_ctx* ctx, int64_t* h2d, int64_t* d2
     return SSB_OK;
 }
 
-extern "C" int ssb_pcm16_decode(ssb_ctx* ctx, const int16_t* d_in, int64_t n, float* d_out, void* stream) {
+static int ssb_pcm16_decode_impl(ssb_ctx* ctx, const int16_t* d_in, int64_t n, float* d_out, void* stream) {
     if (!ctx) return SSB_E_INVALID_ARG;
     if (n == 0) return SSB_OK;
     if (n < 0 || !d_in || !d_out) SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_pcm16_decode: bad arguments");
@@ -1620,7 +1660,7 @@ extern "C" int ssb_pcm16_decode(ssb_ctx* ctx, const int16_t* d_in, int64_t n, fl
     return SSB_OK;
 }
 
-extern "C" int ssb_pcm16_encode(ssb_ctx* ctx, const float* d_in, int64_t n, int mode, int16_t* d_out, void* stream) {
+static int ssb_pcm16_encode_impl(ssb_ctx* ctx, const float* d_in, int64_t n, int mode, int16_t* d_out, void* stream) {
     if (!ctx) return SSB_E_INVALID_ARG;
     if (n == 0) return SSB_OK;
     if (n < 0 || !d_in || !d_out || (mode != 0 && mode != 1)) SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_pcm16_encode: bad arguments");
@@ -1630,4 +1670,68 @@ extern "C" int ssb_pcm16_encode(ssb_ctx* ctx, const float* d_in, int64_t n, int 
     ctx->launches += 1;
     SSB_CUDA(ctx, cudaGetLastError());
     return SSB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI entries: device guard + exception barrier around the implementations above
+// ---------------------------------------------------------------------------
+extern "C" int ssb_get_kernel_timing(ssb_ctx* ctx, double* ms_sum, int64_t* counts) {
+    return abi_call(ctx, [&] { return ssb_get_kernel_timing_impl(ctx, ms_sum, counts); });
+}
+
+extern "C" int ssb_source_windows(ssb_ctx* ctx, const ssb_plan* plan, const float* d_src, int S, int64_t m0, int wrap,
+                                  int nw, int wofs, void* d_x, void* stream) {
+    return abi_call(ctx, [&] { return ssb_source_windows_impl(ctx, plan, d_src, S, m0, wrap, nw, wofs, d_x, stream); });
+}
+
+extern "C" int ssb_convolve_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs,
+                                  const float* d_rir_bank, const void* d_xpool, void* d_hscratch, float* d_wave,
+                                  int64_t wave_stride, void* stream) {
+    return abi_call(ctx, [&] { return ssb_convolve_batch_impl(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_hscratch, d_wave, wave_stride, stream); });
+}
+
+extern "C" int ssb_crossfade_batch(ssb_ctx* ctx, int B, const float* d_prev, float* d_cur, int sr, int64_t wave_stride,
+                                   const uint8_t* d_enable, void* stream) {
+    return abi_call(ctx, [&] { return ssb_crossfade_batch_impl(ctx, B, d_prev, d_cur, sr, wave_stride, d_enable, stream); });
+}
+
+extern "C" int ssb_spectrogram_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int pad_mode,
+                                     float* d_spec, void* stream) {
+    return abi_call(ctx, [&] { return ssb_spectrogram_batch_impl(ctx, B, d_wave, wave_stride, sr, pad_mode, d_spec, stream); });
+}
+
+extern "C" int ssb_render_batch(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs, const float* d_rir_bank,
+                                const void* d_xpool, void* d_hscratch, float* d_wave, int64_t wave_stride, int pad_mode,
+                                float* d_spec, void* stream) {
+    return abi_call(ctx, [&] { return ssb_render_batch_impl(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_hscratch, d_wave, wave_stride, pad_mode, d_spec, stream); });
+}
+
+extern "C" int ssb_render_batch_host(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* h_reqs, const float* h_rir,
+                                     int64_t rir_bytes, float* d_rir_staging, ssb_req* d_reqs_staging, const void* d_xpool,
+                                     void* d_hscratch, float* d_wave, int64_t wave_stride, int pad_mode, float* d_spec,
+                                     float* h_spec, float* h_wave, int n_chunks, void* stream) {
+    return abi_call(ctx, [&] { return ssb_render_batch_host_impl(ctx, plan, B, h_reqs, h_rir, rir_bytes, d_rir_staging, d_reqs_staging, d_xpool, d_hscratch, d_wave, wave_stride, pad_mode, d_spec, h_spec, h_wave, n_chunks, stream); });
+}
+
+extern "C" int ssb_sh_decode_batch(ssb_ctx* ctx, int B, const float* d_amb, int L, const float* d_az_deg, const float* d_hbank,
+                                   void* d_filters, float* d_out_rir, void* stream) {
+    return abi_call(ctx, [&] { return ssb_sh_decode_batch_impl(ctx, B, d_amb, L, d_az_deg, d_hbank, d_filters, d_out_rir, stream); });
+}
+
+extern "C" int ssb_logmel_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int n_mels, int power,
+                                int pad_mode, float* d_out, void* stream) {
+    return abi_call(ctx, [&] { return ssb_logmel_batch_impl(ctx, B, d_wave, wave_stride, sr, n_mels, power, pad_mode, d_out, stream); });
+}
+
+extern "C" int ssb_intensity_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int num_frame,
+                                   float* d_out, void* stream) {
+    return abi_call(ctx, [&] { return ssb_intensity_batch_impl(ctx, B, d_wave, wave_stride, sr, num_frame, d_out, stream); });
+}
+
+extern "C" int ssb_pcm16_decode(ssb_ctx* ctx, const int16_t* d_in, int64_t n, float* d_out, void* stream) {
+    return abi_call(ctx, [&] { return ssb_pcm16_decode_impl(ctx, d_in, n, d_out, stream); });
+}
+
+extern "C" int ssb_pcm16_encode(ssb_ctx* ctx, const float* d_in, int64_t n, int mode, int16_t* d_out, void* stream) {
+    return abi_call(ctx, [&] { return ssb_pcm16_encode_impl(ctx, d_in, n, mode, d_out, stream); });
 }

@@ -73,13 +73,61 @@ def _dev_index(device):
     return torch.cuda.current_device() if device.index is None else device.index
 
 
+class WaveformOps:
+    """Kernels that only need a context -- the STFT front end and the AV-WaN intensity reduction on waveforms the
+    caller already holds -- without a convolution plan, RIR bank or window-spectra pool.  One per device; this is
+    what ``SpectrogramSensor.compute_spectrogram`` (a static method other modules import and call on host arrays of
+    any length, savi/ppo/ppo_trainer.py:52,374, belief_predictor.py:15,124) runs on."""
+
+    _instances: dict = {}
+
+    def __init__(self, device="cuda:0"):
+        self.device = torch.device("cuda", _dev_index(device))
+        self.ctx = _lib.Context(self.device.index)
+        self.lib = self.ctx.lib
+
+    @classmethod
+    def get(cls, device="cuda:0") -> "WaveformOps":
+        key = _dev_index(device)
+        if key not in cls._instances:
+            cls._instances[key] = cls(torch.device("cuda", key))
+        return cls._instances[key]
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def spectrogram(self, wave: torch.Tensor, pad_mode: str = "reflect", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(n, 2, S) CUDA float32 -> (n, 65, T', 2) for any S >= 512 (nav.py:86-100)."""
+        if wave.ndim == 2:
+            wave = wave[None]
+        wave = wave.to(self.device, torch.float32).contiguous()
+        n, _, S = wave.shape
+        spec = out if out is not None else torch.empty((n,) + spectrogram_shape(S), dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.ssb_spectrogram_batch(self.ctx.handle, n, wave.data_ptr(), S, S, PAD_MODES[pad_mode],
+                                                      spec.data_ptr(), self._stream()), "ssb_spectrogram_batch")
+        return spec
+
+    def intensity(self, wave: torch.Tensor, num_frame: int = 150) -> torch.Tensor:
+        """AV-WaN ``Intensity`` (avwan_sensors.py:91-100) for a (n, 2, S) CUDA batch -> (n,) mean squares."""
+        if wave.ndim == 2:
+            wave = wave[None]
+        wave = wave.to(self.device, torch.float32).contiguous()
+        out = torch.empty(wave.shape[0], dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.ssb_intensity_batch(self.ctx.handle, wave.shape[0], wave.data_ptr(), wave.shape[2],
+                                                    wave.shape[2], int(num_frame), out.data_ptr(), self._stream()),
+                       "ssb_intensity_batch")
+        return out
+
+
 class BatchedAudioRenderer:
     def __init__(self, sr: int, max_taps: int, device="cuda:0", n_terms: int = 1, log2n: int = 0,
                  pad_mode: str = "reflect", xpool_bytes: int = 512 << 20):
         self.sr = int(sr)
         self.device = torch.device("cuda", _dev_index(device))
         self.pad_mode = PAD_MODES[pad_mode]
-        torch.cuda.set_device(self.device)
+        # No global side effect: the caller's current CUDA device is left alone.  Every C-ABI entry selects the
+        # context's device itself (and restores the caller's); tensors are allocated with an explicit device and
+        # streams are taken from torch's current stream OF THAT device.
         self.ctx = _lib.Context(self.device.index)
         self.lib = self.ctx.lib
         self.max_taps = int(max_taps)
@@ -96,13 +144,22 @@ class BatchedAudioRenderer:
         self._bank_index = None               # numpy copies of the two lists, rebuilt when the bank changes
         # sources + window-spectra pool
         self._sources: list[torch.Tensor] = []
-        self._xpool = torch.empty(max(xpool_bytes // 8, 64 * self.N) * 2, dtype=torch.float32, device=self.device)
+        # window-spectra pool: allocated on first use (a renderer that only runs the STFT / intensity kernels on
+        # waveforms it is handed -- SpectrogramSensor.compute_spectrogram on a host array -- never needs it)
+        self._xpool_elems = max(xpool_bytes // 8, 64 * self.N)      # float2 elements
+        self._xpool_t = None
         self._xpool_used = 0                  # float2 elements
         self._xcache: dict = {}
         self._hscratch = None
         self._wave = None
         self._prev_wave = None
         self._hbank = None
+
+    @property
+    def _xpool(self) -> torch.Tensor:
+        if self._xpool_t is None:
+            self._xpool_t = torch.empty(self._xpool_elems * 2, dtype=torch.float32, device=self.device)
+        return self._xpool_t
 
     def set_conv_mode(self, mode: int):
         """0 = per-bin partition sums then inverse FFTs (default); 1 = fused into the inverse-FFT kernel."""
@@ -118,33 +175,58 @@ class BatchedAudioRenderer:
 
     # ------------------------------------------------------------------ banks
     def add_rirs(self, rirs: Sequence) -> list:
-        """Append RIRs ((L, 2) float32 arrays / tensors; None or empty => zero-RIR fallback)."""
-        ids, chunks, total = [], [], 0
-        self._bank_index = None
+        """Append RIRs ((L, 2) float32 arrays / tensors; None or empty => zero-RIR fallback).
+        All-or-nothing: every entry is validated and converted BEFORE the index lists or the bank are touched,
+        so a bad entry in the middle of the list leaves the bank exactly as it was."""
+        offs, lens, chunks, total = [], [], [], 0
         for r in rirs:
             if r is None or len(r) == 0:
-                self._rir_off.append(0)
-                self._rir_len.append(0)
-            else:
-                t = torch.as_tensor(r, dtype=torch.float32)
-                if t.ndim != 2 or t.shape[1] != 2:
-                    raise ValueError(f"RIR must be (L, 2), got {tuple(t.shape)}")
-                self._rir_off.append(self._bank_used + total)
-                self._rir_len.append(t.shape[0])
-                chunks.append(t)
-                total += t.shape[0]
-            ids.append(len(self._rir_off) - 1)
+                offs.append(0)
+                lens.append(0)
+                continue
+            t = torch.as_tensor(r, dtype=torch.float32)
+            if t.ndim != 2 or t.shape[1] != 2:
+                raise ValueError(f"RIR must be (L, 2), got {tuple(t.shape)}")
+            offs.append(self._bank_used + total)
+            lens.append(t.shape[0])
+            chunks.append(t)
+            total += t.shape[0]
         if total:
             need = self._bank_used + total
             if need > self._bank.shape[0]:
                 grown = torch.empty((max(need, 2 * self._bank.shape[0]), 2), dtype=torch.float32, device=self.device)
                 grown[: self._bank_used] = self._bank[: self._bank_used]
                 self._bank = grown
-            host = torch.cat([c.cpu() if c.is_cuda else c for c in chunks]) if not all(c.is_cuda for c in chunks) \
-                else torch.cat(chunks)
+            if all(c.is_cuda for c in chunks):
+                host = torch.cat(chunks)
+            else:
+                host = torch.cat([c.cpu() if c.is_cuda else c for c in chunks])
             self._bank[self._bank_used: need].copy_(host, non_blocking=True)
             self._bank_used = need
-        return ids
+        first = len(self._rir_off)
+        self._rir_off.extend(offs)
+        self._rir_len.extend(lens)
+        self._bank_index = None
+        return list(range(first, first + len(offs)))
+
+    def compact_bank(self, keep_ids: Sequence[int]) -> list:
+        """Keep only the given RIRs (one device-side gather into a fresh arena) and return their new ids, in the
+        order given; every other id becomes invalid.  The file-backed service calls this when the resident bank
+        outgrows its budget, keeping the recently used part of the working set instead of re-reading it."""
+        keep_ids = [int(i) for i in keep_ids]
+        lens = [self._rir_len[i] for i in keep_ids]
+        total = sum(lens)
+        arena = torch.empty((max(total, 1), 2), dtype=torch.float32, device=self.device)
+        offs, pos = [], 0
+        for i, n in zip(keep_ids, lens):
+            offs.append(pos if n else 0)
+            if n:
+                arena[pos: pos + n].copy_(self._bank[self._rir_off[i]: self._rir_off[i] + n])
+                pos += n
+        self._bank, self._bank_used = arena, total
+        self._rir_off, self._rir_len = offs, lens
+        self._bank_index = None
+        return list(range(len(keep_ids)))
 
     def reset_bank(self):
         """Forget every RIR (ids become invalid).  Used by the file-backed service when the resident
@@ -420,6 +502,22 @@ class BatchedAudioRenderer:
             self._xpool.data_ptr(), hs.data_ptr(), wave.data_ptr(), self.sr,
             self.pad_mode | (0x100 if channels_first else 0), spec.data_ptr(), self._stream()), "ssb_render_batch")
         return (spec, wave) if want_wave else spec
+
+    @contextlib.contextmanager
+    def transient_windows(self):
+        """Window-spectra sets created inside the block are dropped at its end (stack discipline, like
+        :meth:`bank_mark` / :meth:`bank_release` for RIRs).  The continuous simulator asks for a new
+        ``(clip, sample offset)`` every step; without this each step would leave a dead set behind until the pool
+        overflowed and was reset wholesale with a stream synchronise.  Safe while kernels are in flight: the next
+        ``ssb_source_windows`` into the reclaimed space is ordered after them on the same stream."""
+        used, keys = self._xpool_used, set(self._xcache)
+        try:
+            yield
+        finally:
+            if self._xpool_used >= used:                  # not recycled meanwhile
+                for k in [k for k in self._xcache if k not in keys]:
+                    del self._xcache[k]
+                self._xpool_used = used
 
     @contextlib.contextmanager
     def _inline_rirs(self, *request_lists):
