@@ -231,6 +231,80 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------- GPU arm
+MIN_REGION_S = 0.05          # a timed region shorter than this is repeated and the median reported
+
+
+def timed_region(step, steps, barrier, torch, first_index=0):
+    """CUDA-event time of exactly `steps` calls of step(i), barrier + synchronize on both sides.  When the region is
+    shorter than MIN_REGION_S it is repeated (same K steps each time) and the MEDIAN is returned, so that a 20-step
+    run of a 0.1 ms step is not a 2 ms sample.  Returns (ms of one K-step region, repeats, total timed seconds)."""
+    def once():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            step(first_index + i)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+    first = once()
+    reps = 1
+    if first * 1e-3 < MIN_REGION_S:
+        reps = int(min(200, max(3, np.ceil(MIN_REGION_S / max(first * 1e-3, 1e-6)) + 1))) | 1      # odd
+    times = [first] + [once() for _ in range(reps - 1)]
+    return float(np.median(times)), reps, float(np.sum(times)) * 1e-3
+
+
+def numa_bind(local_rank, torch):
+    """Bind this rank (and therefore the pinned buffers it allocates afterwards, first touch) to the CPUs of the
+    NUMA node its GPU hangs off: eight unpinned ranks pushing 16 MB per step through one socket's memory is what held
+    the round-1 end-to-end scaling at 0.67.  Best effort: returns a description or the reason it did nothing."""
+    try:
+        from soundspaces_b200.distributed import gpu_numa_cpus
+        node, cpus = gpu_numa_cpus(local_rank)
+        if node is None or not cpus:
+            return "no NUMA information for this GPU"
+        allowed = os.sched_getaffinity(0)
+        use = sorted(set(cpus) & set(allowed))
+        if not use:
+            return f"NUMA node {node}: none of its CPUs is in this process's cpuset"
+        os.sched_setaffinity(0, use)
+        return f"rank bound to NUMA node {node} ({len(use)} CPUs)"
+    except Exception as e:          # noqa: BLE001
+        return "not bound: " + repr(e)[:80]
+
+
+# per-step LIVE traffic of the whole path: `ncu --replay-mode range --cache-control none` around one steady-state step
+# of this workload (both internal streams running concurrently, caches as the previous steps left them); committed captures
+LIVE_TRAFFIC = {
+    "partitioned": {"dram_bytes": 17839616 + 162457088, "l2_bytes": 661364256, "source": "profiles/live_traffic_r02_base_1step.csv"},
+    "block64": None,   # filled in from profiles/live_traffic_r02_block64_1step.csv once captured (see LIVE_TRAFFIC_BLOCK64)
+}
+LIVE_TRAFFIC_BLOCK64 = os.path.join(ROOT, "profiles", "live_traffic_r02_block64_1step.csv")
+# FMA-pipe cycles per SM and executed warp-instructions per launch from committed `ncu --set full` captures, by kernel
+# (64-env launches of the C2 workload): the compute roofline this FP32 path really has
+NCU_PER_LAUNCH = os.path.join(ROOT, "profiles", "ncu_per_launch.json")
+
+
+def read_live_traffic(path):
+    try:
+        vals = {}
+        for line in open(path):
+            p = [x.strip('"') for x in line.strip().split('","')]
+            if len(p) > 3 and p[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum"):
+                vals[p[-3]] = float(p[-1].replace(",", "").strip('"'))
+        return {"dram_bytes": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"], "l2_bytes": vals.get("lts__t_bytes.sum"),
+                "source": os.path.relpath(path, ROOT)}
+    except Exception:
+        return None
+
+
+def alg_bytes(taps_eff, src_samples, share, sr):
+    """8*L_eff + 4*S_seg/B_share + 8*65*T' (spectrogram-only output)."""
+    cols = -(-(1 + sr // 160) // 4)
+    return 8 * taps_eff + 4 * src_samples // max(share, 1) + 8 * 65 * cols
+
+
 def run_gpu(args, rank, local_rank, world):
     # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL prints its version there)
     # are sent to stderr for the duration of the run
@@ -238,9 +312,10 @@ def run_gpu(args, rank, local_rank, world):
     json_fd = os.dup(1)
     os.dup2(2, 1)
     import torch
+    numa = numa_bind(local_rank, torch) if (world > 1 and not args.no_numa) else "single rank: not bound"
     import torch.distributed as dist
     from soundspaces_b200 import AudioRequest, BatchedAudioRenderer
-    from synth import make_source
+    from synth import make_rir, make_source
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -248,21 +323,28 @@ def run_gpu(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
 
     B = ENVS_PER_GPU
-    r = BatchedAudioRenderer(SR, TAPS, device=dev, log2n=args.log2n)
+    r = BatchedAudioRenderer(SR, TAPS, device=dev, log2n=args.log2n, prefer_block64=(args.plan == "block64"))
     r.set_conv_mode(args.conv_mode)
     sid = r.add_source(make_source(7, SR))
     bank_host = make_bank_host(N_BANKS * B, seed0=rank)
     bank = torch.from_numpy(bank_host).to(dev)
     ids = r.set_dense_rir_bank(bank)
     sil = silent_mask(B, seed0=rank)
-    batches = [r.prepare([AudioRequest(rir=ids[k * B + i], source=sid, silent=bool(sil[i])) for i in range(B)])
-               for k in range(N_BANKS)]
+    req_lists = [[AudioRequest(rir=ids[k * B + i], source=sid, silent=bool(sil[i])) for i in range(B)] for k in range(N_BANKS)]
+    batches = [r.prepare(q) for q in req_lists]
+    path = "block64" if batches[0].plan.log2n == 16 else "partitioned"
     spec_out = torch.empty((B,) + r.spec_shape, dtype=torch.float32, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def step(i):
         r.execute(batches[i % N_BANKS], out=spec_out)
@@ -276,18 +358,12 @@ def run_gpu(args, rank, local_rank, world):
         sampler.start()
         time.sleep(0.25)
     launches0 = r.ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     t_wall0 = time.time()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
+    ms, reps, region_s = timed_region(step, args.steps, barrier, torch)
     t_wall1 = time.time()
-    ms = e0.elapsed_time(e1)
-    launches = r.ctx.launch_count - launches0
+    launches = (r.ctx.launch_count - launches0) // reps
     # a long enough region for the clock sampler: keep the GPU under the same load for >= 1.5 s
+    clocks = None
     if sampler:
         t_end = time.time() + max(0.0, 1.5 - (t_wall1 - t_wall0))
         i = 0
@@ -297,46 +373,43 @@ def run_gpu(args, rank, local_rank, world):
             torch.cuda.synchronize()
         t_wall1 = time.time()
         clocks = sampler.stop(t_wall0, t_wall1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = allmax(ms)
 
-    # ---- optional centralised-policy mode: every step ends with ONE in-place all-gather of the
-    # observation batch; the spectrogram kernel writes straight into this rank's slice of the gather buffer
+    # ---- centralised-policy mode: every step ends with ONE in-place all-gather of the observation
+    # batch; the spectrogram kernel writes straight into this rank's slice of the gather buffer
     gather_info = None
-    if world > 1 and args.gather:
+    if world > 1 and not args.no_gather:
         try:
             from soundspaces_b200.distributed import GatheredObservations
             gobs = GatheredObservations(B * world, r.spec_shape, rank, world, dev)
             assert gobs.n_local == B
+            state = {}
 
             def gstep(i):
                 r.execute(batches[i % N_BANKS], out=gobs.local)
-                return gobs.gather()
+                state["flat"] = gobs.gather()
 
             for i in range(max(3, args.warmup // 2)):
                 gstep(i)
-            barrier()
-            ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ge0.record()
-            for i in range(args.steps):
-                flat = gstep(i)
-            ge1.record()
-            barrier()
-            tg = torch.tensor([ge0.elapsed_time(ge1)], dtype=torch.float64, device=dev)
-            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-            # every rank must now hold every rank's rows: compare a checksum of the gathered batch across ranks
+            gms, greps, _ = timed_region(gstep, args.steps, barrier, torch)
+            gms = allmax(gms)
+            # every rank must now hold every rank's rows: compare a checksum of the gathered batch across ranks,
+            # and this rank's own rows with what it rendered without the collective
+            flat = state["flat"]
             chk = flat.double().sum().reshape(1)
             lo, hi = chk.clone(), chk.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-            gather_info = {"value": B * world * args.steps / (float(tg.item()) * 1e-3), "unit": UNIT,
-                           "ms_per_step": float(tg.item()) / args.steps,
+            r.execute(batches[(args.steps - 1) % N_BANKS], out=spec_out)
+            own = torch.tensor([float(torch.equal(gobs.local, spec_out))], device=dev)
+            dist.all_reduce(own, op=dist.ReduceOp.MIN)
+            gather_info = {"value": B * world * args.steps / (gms * 1e-3), "unit": UNIT,
+                           "ms_per_step": gms / args.steps, "cost_ms_per_step": gms / args.steps - ms_max / args.steps,
                            "bytes_sent_per_rank_per_step": int(gobs.local.numel() * 4),
                            "collective": "one in-place ncclAllGather per step (all_gather_into_tensor on the buffer the "
                                          "spectrogram kernel wrote into)",
-                           "identical_on_all_ranks": bool(float(lo.item()) == float(hi.item()))}
+                           "identical_on_all_ranks": bool(float(lo.item()) == float(hi.item())),
+                           "local_rows_bit_identical_to_ungathered": bool(own.item() == 1.0)}
         except Exception as e:          # informational leg: never take the headline measurement down with it
             gather_info = {"error": repr(e)[:200]}
 
@@ -353,20 +426,112 @@ def run_gpu(args, rank, local_rank, world):
     hs.set_requests(sid, silent=sil)
     for _ in range(max(3, args.warmup // 4)):
         hs.run()
-    barrier()
-    e2e_steps = args.steps
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(e2e_steps):
-        hs.run()
-    g1.record()
-    barrier()
-    e2e_ms = g0.elapsed_time(g1)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(t.item())
+    e2e_ms, _, _ = timed_region(lambda i: hs.run(), args.steps, barrier, torch)
+    e2e_ms_max = allmax(e2e_ms)
     checksum = float(hs.h_spec.double().sum())
+    hs_bytes = (hs.h2d_bytes, hs.d2h_bytes)
+
+    # ---- end to end with a device-resident RIR bank and a stated miss rate (what training does once the
+    # scene's working set is resident: per step only the MISSING RIRs cross PCIe, the spectrograms come back)
+    miss_info = None
+    try:
+        miss = args.miss_rate
+        n_miss = max(1, int(round(miss * B)))
+        h_miss = torch.from_numpy(bank_host[:n_miss].copy()).pin_memory()
+        d_miss = [torch.empty((n_miss, TAPS, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        h_spec = torch.empty((B,) + r.spec_shape, dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        ev = [torch.cuda.Event() for _ in range(2)]
+
+        def mstep(i):
+            k = i & 1
+            with torch.cuda.stream(copy_stream):                    # the misses of step i+1 travel during step i
+                d_miss[k].copy_(h_miss, non_blocking=True)
+                ev[k].record(copy_stream)
+            torch.cuda.current_stream(dev).wait_event(ev[k])
+            # the uploaded rows replace the first n_miss rows of this step's bank slice (same request array)
+            bank[(i % N_BANKS) * B: (i % N_BANKS) * B + n_miss].copy_(d_miss[k], non_blocking=True)
+            r.execute(batches[i % N_BANKS], out=spec_out)
+            h_spec.copy_(spec_out, non_blocking=True)
+
+        for i in range(5):
+            mstep(i)
+        mms, _, _ = timed_region(mstep, args.steps, barrier, torch)
+        mms = allmax(mms)
+        miss_info = {"value": B * world * args.steps / (mms * 1e-3), "unit": UNIT, "ms_per_step": mms / args.steps,
+                     "miss_rate": n_miss / B, "h2d_bytes_per_step": int(n_miss * TAPS * 8),
+                     "d2h_bytes_per_step": int(h_spec.numel() * 4),
+                     "what": "device-resident bank; per step the missing RIRs are copied from pinned host memory on a copy "
+                             "stream (overlapping the previous step's kernels) and the spectrograms are read back"}
+        bank.copy_(torch.from_numpy(bank_host))                      # restore for the legs below
+        torch.cuda.synchronize()
+    except Exception as e:          # noqa: BLE001
+        miss_info = {"error": repr(e)[:200]}
+
+    # ---- the public API paths: per step host work included
+    api_info = {}
+    try:
+        def api_step(i):                                            # render(list[AudioRequest]): prepare() every step
+            r.execute(r.prepare(req_lists[i % N_BANKS]), out=spec_out)
+        for i in range(5):
+            api_step(i)
+        ams, _, _ = timed_region(api_step, args.steps, barrier, torch)
+        rir_arr = [np.asarray(ids[k * B:(k + 1) * B], dtype=np.int64) for k in range(N_BANKS)]
+
+        def arr_step(i):                                            # prepare_arrays(): requests held as arrays
+            r.execute(r.prepare_arrays(rir_arr[i % N_BANKS], sid, silent=sil), out=spec_out)
+        for i in range(5):
+            arr_step(i)
+        bms, _, _ = timed_region(arr_step, args.steps, barrier, torch)
+        api_info = {"api_path": {"value": B * world * args.steps / (allmax(ams) * 1e-3), "unit": UNIT,
+                                 "what": "execute(prepare(list[AudioRequest])) every step: request resolution + H2D of the request array + launches"},
+                    "api_path_arrays": {"value": B * world * args.steps / (allmax(bms) * 1e-3), "unit": UNIT,
+                                        "what": "execute(prepare_arrays(...)) every step: requests held as numpy columns"}}
+    except Exception as e:          # noqa: BLE001
+        api_info = {"api_path": {"error": repr(e)[:200]}}
+    try:
+        api_info["plugin_path"] = plugin_path_leg(args, r, bank_host, sid, dev, world, barrier, allmax, torch)
+    except Exception as e:          # noqa: BLE001
+        api_info["plugin_path"] = {"error": repr(e)[:200]}
+
+    # ---- the other convolution plan on the same workload (N = 1): the single-block cluster kernel trades step time
+    # for DRAM traffic (no H / Y intermediates); reported next to the headline, which uses the faster plan
+    alt = None
+    if world == 1 and not args.no_extra:
+        try:
+            other = "partitioned" if path == "block64" else "block64"
+            r2 = BatchedAudioRenderer(SR, TAPS, device=dev, prefer_block64=(other == "block64"))
+            sid2 = r2.add_source(make_source(7, SR))
+            ids2 = r2.set_dense_rir_bank(bank)
+            b2 = [r2.prepare([AudioRequest(rir=ids2[k * B + i], source=sid2, silent=bool(sil[i])) for i in range(B)]) for k in range(N_BANKS)]
+            out2 = torch.empty_like(spec_out)
+
+            def step2(i):
+                r2.execute(b2[i % N_BANKS], out=out2)
+            for i in range(args.warmup):
+                step2(i)
+            ms2, reps2, _ = timed_region(step2, args.steps, barrier, torch)
+            r2.ctx.set_kernel_timing(True)
+            for i in range(args.steps):
+                step2(i)
+            kt2 = r2.ctx.get_kernel_timing()
+            r2.ctx.set_kernel_timing(False)
+            step(0); step2(0)
+            torch.cuda.synchronize()
+            live2 = (read_live_traffic(LIVE_TRAFFIC_BLOCK64) if other == "block64" else LIVE_TRAFFIC["partitioned"])
+            alt = {"plan": other, "value": B * args.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps, "repeats": reps2,
+                   "kernel_ms_all": {k: v[0] / args.steps for k, v in kt2.items() if v[1]},
+                   "traffic": live2["dram_bytes"] if live2 else None, "traffic_source": live2["source"] if live2 else None,
+                   "traffic_over_algorithmic": (live2["dram_bytes"] / (ALG_BYTES_PER_FRAME * B)) if live2 else None,
+                   "max_abs_diff_vs_headline_plan": float((out2 - spec_out).abs().max())}
+            del r2, b2
+        except Exception as e:          # noqa: BLE001
+            alt = {"error": repr(e)[:200]}
+
+    extra = None
+    if world == 1 and not args.no_extra:
+        del hs
+        extra = extra_workloads(args, dev, torch, barrier)
 
     if rank == 0:
         frames = B * world * args.steps
@@ -376,7 +541,7 @@ def run_gpu(args, rank, local_rank, world):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-        hot = [k for k in ("fwd_rir_kernel", "mac_bins_kernel", "mac_ifft_kernel", "spectrogram_kernel") if ktimes[k][1]]
+        hot = [k for k in ("fwd_rir_kernel", "mac_bins_kernel", "mac_ifft_kernel", "conv64k_kernel", "spectrogram_kernel") if ktimes[k][1]]
         # per STEP: a kernel may be launched several times per step (sub-batches on internal streams)
         per_step_ms = {k: ktimes[k][0] / args.steps for k in hot}
         launches_per_step = {k: ktimes[k][1] / args.steps for k in hot}
@@ -386,29 +551,39 @@ def run_gpu(args, rank, local_rank, world):
         achieved = alg_bytes_launch / (dom_ms * 1e-3) / 1e9
         step_ms = ms_max / args.steps
         kernel_sum = sum(per_step_ms.values())
-        # compute roofline of the kernels as built (default plan only): the time the FMA pipes / the issue slots need
-        # for one step's instructions (counts from profiles/prof_r01d.ncu-rep) over the measured step time
+        live = (read_live_traffic(LIVE_TRAFFIC_BLOCK64) if path == "block64" else None) or (LIVE_TRAFFIC[path] if path == "partitioned" else None)
+        # compute roofline of the kernels as built: the time the FMA pipes / the issue slots need for one step's
+        # instructions (counts per launch from the committed ncu capture) over the measured step time
         fma_frac = issue_frac = None
         try:
-            if args.log2n in (0, 12) and args.conv_mode == 0:
-                sm_mhz = (clocks.get("sm_mhz") or 1965.0)
-                sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-                fma_frac = (sum(NCU_FMA_PIPE_CYCLES_PER_LAUNCH[k] * launches_per_step[k] for k in hot)
-                            / (sm_mhz * 1e6) / (step_ms * 1e-3))
-                issue_frac = (sum(NCU_WARP_INST_PER_LAUNCH[k] * launches_per_step[k] for k in hot)
-                              / (sm_count * 4) / (sm_mhz * 1e6) / (step_ms * 1e-3))
+            per_launch = json.load(open(NCU_PER_LAUNCH))[path]
+            sm_mhz = ((clocks or {}).get("sm_mhz") or 1965.0)
+            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+            fma_frac = (sum(per_launch[k]["fma_pipe_cycles_per_sm"] * launches_per_step[k] for k in hot)
+                        / (sm_mhz * 1e6) / (step_ms * 1e-3))
+            issue_frac = (sum(per_launch[k]["warp_instructions"] * launches_per_step[k] for k in hot)
+                          / (sm_count * 4) / (sm_mhz * 1e6) / (step_ms * 1e-3))
         except Exception:
             pass
+        cfg = workload_config(world)
+        cfg["convolution_plan"] = ("single block: one fused 65536-point cluster kernel per env (conv64k_kernel)" if path == "block64"
+                                   else "partitioned overlap-save (fwd_rir / mac_bins / mac_ifft)")
+        cfg["numa"] = numa
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "timed_region_s": region_s, "timed_region_repeats": reps,
+            "timed_region_note": f"the K={args.steps}-step region was timed {reps} time(s); ms_per_step is the median region / K",
             "roofline": {
                 "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom, 0.0) * launches_per_step[dom] if args.log2n in (0, 12) else None,
-                "traffic_source": "profiles/prof_r01d.ncu-rep: dram__bytes_read.sum + dram__bytes_write.sum of the "
-                                  "dominant kernel (cold-cache replay, 64-env launch) x its launches per step",
+                "traffic": live["dram_bytes"] if live else None,
+                "traffic_source": (live["source"] + ": dram__bytes_read.sum + dram__bytes_write.sum of ONE LIVE STEP of this workload "
+                                   "(all kernels of the step, ncu range replay without cache control), to be read against "
+                                   "algorithmic_bytes_per_step") if live else None,
+                "traffic_over_algorithmic": (live["dram_bytes"] / alg_bytes_launch) if live else None,
+                "l2_bytes_per_step": live.get("l2_bytes") if live else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_step": alg_bytes_launch, "kernel_ms": dom_ms,
                 "kernel_ms_all": per_step_ms, "kernel_launches_per_step": launches_per_step,
@@ -417,21 +592,28 @@ def run_gpu(args, rank, local_rank, world):
                 "kernel_share_of_step": dom_ms / max(kernel_sum, 1e-9),
                 "path_achieved_gbs": alg_bytes_launch / (step_ms * 1e-3) / 1e9,
                 "path_frac_hbm": alg_bytes_launch / (step_ms * 1e-3) / 1e9 / peak,
-                "fp32_frac": (value / world) * ALG_FLOP_PER_FRAME / (FP32_PEAK_TFLOPS * 1e12),
+                "fp32_frac_nominal": (value / world) * ALG_FLOP_PER_FRAME / (FP32_PEAK_TFLOPS * 1e12),
+                "fp32_lane_op_peak_measured": "36.6e12 FP32-pipe lane-ops/s (FADD2 / FFMA2 issue rate, profiles/f32x2_bench_r02.log): an "
+                                              "add-dominated FFT can at most reach 36.6 TFLOP/s, not the 73 TFLOP/s of pure FMA code",
                 "fma_pipe_frac": fma_frac, "issue_slot_frac": issue_frac,
                 "note": "FFT work is FP32-pipe bound (about 100 flop/B at algorithmic traffic): fma_pipe_frac / issue_slot_frac are the "
-                        "fractions that measure kernel quality; the launch sizes of the capture are 64-env sub-batches, the same "
-                        "as the 2 launches per kernel per step here; see DESIGN.md",
+                        "fractions that measure kernel quality; see DESIGN.md",
             },
-            "e2e": {"value": B * world * e2e_steps / (e2e_ms_max * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes,
-                    "ms_per_step": e2e_ms_max / e2e_steps, "api": f"ssb_render_batch_host (pinned host RIRs in, host spectrograms out), {args.chunks} pipelined chunks",
+            "e2e": {"value": B * world * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": hs_bytes[0], "d2h_bytes_per_step": hs_bytes[1],
+                    "ms_per_step": e2e_ms_max / args.steps, "api": f"ssb_render_batch_host (pinned host RIRs in, host spectrograms out), {args.chunks} pipelined chunks",
                     "checksum": checksum},
+            "e2e_resident_bank": miss_info,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        line.update(api_info)
         if gather_info is not None:
             line["with_allgather"] = gather_info
+        if alt is not None:
+            line["alternative_plan"] = alt
+        if extra is not None:
+            line["extra_workloads"] = extra
         if world == 1 and not args.no_cpu:
             cores = usable_cpus()
             v, n, dt = cpu_throughput(cores * args.cpu_frames_per_core, cores)
@@ -444,6 +626,146 @@ def run_gpu(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def plugin_path_leg(args, r, bank_host, sid, dev, world, barrier, allmax, torch):
+    """Frames/s through the per-env plugin surface: SpectrogramSensor.get_observation per env (deferred handles) +
+    batch_obs, every env at a NEW grid node every step (100 % memo miss, resident RIRs)."""
+    from soundspaces_b200.replay import ReplayScene, ReplaySim, ReplayVectorEnv
+    from soundspaces_b200.sensors import batch_obs
+    from soundspaces_b200.simulator import AudioRenderService
+    from synth import make_source
+    B = ENVS_PER_GPU
+    svc = AudioRenderService(SR, device=dev, renderer=r)
+    scene = ReplayScene("bench", side=46)                            # 2116 nodes >= 16 * 128 distinct positions
+    n_rows = bank_host.shape[0]
+    for recv in range(n_rows):                                       # the resident bank rows ARE the scene's RIRs (azimuth 0)
+        svc._rir_ids[(scene.rir_dir, 0, recv, 0)] = recv
+    clip = make_source(7, SR)
+    svc._src_ids[("telephone", len(clip), id(clip))] = (sid, clip)
+    sims = [ReplaySim(svc, scene, "telephone", clip, source_node=0, start_node=i) for i in range(B)]
+    for s in sims:
+        s.b200_prefetch = False
+    envs = ReplayVectorEnv(sims)
+    out = {"spectrogram": torch.empty((B,) + r.spec_shape, dtype=torch.float32, device=dev)}
+
+    def pstep(i):
+        base = (i % N_BANKS) * B
+        for k, s in enumerate(sims):                                 # teleport: every env observes a new node (memo miss)
+            s._receiver_position_index = base + k
+            s._spectrogram_cache = {}
+        batch_obs(envs.observe(), device=dev, out=out)
+
+    for i in range(5):
+        pstep(i)
+    pms, _, _ = timed_region(pstep, args.steps, barrier, torch)
+    pms = allmax(pms)
+    return {"value": B * world * args.steps / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms / args.steps,
+            "what": "per env: SpectrogramSensor.get_observation -> DeferredObservation handle; per step: batch_obs -> ONE render into "
+                    "the rollout slot (128 envs, every env at a new node each step, RIRs resident)"}
+
+
+def extra_workloads(args, dev, torch, barrier):
+    """The other BASELINE.json configs on ONE GPU, inputs resident (same timing rules; short regions are repeated):
+    C3 head / valid / log-mel at 512 envs, C4 (ambisonic decode + convolution) at 256 envs, C5 rollout (16 envs)."""
+    from soundspaces_b200 import AudioRequest, BatchedAudioRenderer
+    from synth import make_source
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    res = {}
+    steps, warm = max(10, min(args.steps, 50)), 5
+    rng = np.random.default_rng(0)
+    sr, L, Bc = 16000, 48000, 512
+
+    def run(name, fn, frames_per_step, bytes_per_frame, flop_per_frame, note):
+        for i in range(warm):
+            fn(i)
+        ms, reps, _ = timed_region(fn, steps, barrier, torch)
+        v = frames_per_step * steps / (ms * 1e-3)
+        res[name] = {"value": v, "unit": UNIT, "ms_per_step": ms / steps, "envs": frames_per_step, "repeats": reps,
+                     "algorithmic_bytes_per_frame": bytes_per_frame, "path_frac_hbm": v * bytes_per_frame / 1e9 / peak,
+                     "algorithmic_flop_per_frame": flop_per_frame, "fp32_frac_nominal": v * flop_per_frame / (FP32_PEAK_TFLOPS * 1e12),
+                     "workload": note}
+    try:
+        r = BatchedAudioRenderer(sr, L, device=dev)
+        env = np.exp(-np.arange(L) / (L / 6.0)).astype(np.float32)
+        banks = [torch.from_numpy((rng.standard_normal((Bc, L, 2)).astype(np.float32) * env[None, :, None] * 0.1)).to(dev) for _ in range(2)]
+        bank = torch.cat(banks)                                          # 2 x 196 MB rotated: larger than L2
+        ids = r.set_dense_rir_bank(bank)
+        s1, s4 = r.add_source(make_source(1, sr)), r.add_source(make_source(2, 4 * sr))
+        out = torch.empty((Bc,) + r.spec_shape, device=dev)
+        head = [r.prepare([AudioRequest(rir=ids[k * Bc + i], source=s1) for i in range(Bc)]) for k in range(2)]
+        valid = [r.prepare([AudioRequest(rir=ids[k * Bc + i], source=s4, offset=3 * sr) for i in range(Bc)]) for k in range(2)]
+        plan = "single-block cluster kernel" if head[0].plan.log2n == 16 else "partitioned"
+        run("C3_head", lambda i: r.execute(head[i & 1], out=out), Bc, alg_bytes(16000, 16000, 64, sr), 7.4e6,
+            f"512 envs, 16 kHz, 1-s clip x 48000-tap RIRs (first 16000 taps matter) -> (65,26,2); {plan}")
+        run("C3_valid", lambda i: r.execute(valid[i & 1], out=out), Bc, alg_bytes(48000, 63999, 64, sr), 13.2e6,
+            f"512 envs, 16 kHz, 4-s clip steady state: all 48000 taps (mode='valid') -> (65,26,2); {plan}")
+        mel_out = torch.empty((Bc,) + r.logmel_shape(64), device=dev)
+
+        def logmel(i):
+            r.logmel(r.convolve_prepared(valid[i & 1]), 64, 2, out=mel_out)
+        run("C3_valid_logmel", logmel, Bc, 8 * 48000 + 4 * 63999 // 64 + 8 * 64 * 101, 13.2e6 + 101 * 2 * 2 * 2 * 257,
+            f"as C3_valid with the log-mel head (64 Slaney mels, power 2; extension, parity unpinned) -> (64,101,2); {plan}")
+        del r, bank, banks
+    except Exception as e:          # noqa: BLE001
+        res["C3_error"] = repr(e)[:200]
+    try:
+        B4 = 256
+        r = BatchedAudioRenderer(sr, L, device=dev)
+        amb = torch.randn((B4, L, 9), device=dev) * 0.05
+        az = torch.tensor([0., 90., 180., 270.] * (B4 // 4))
+        s4 = r.add_source(make_source(2, 4 * sr))
+        out = torch.empty((B4,) + r.spec_shape, device=dev)
+        rirs = r.sh_decode(amb, az)
+        ids = r.set_dense_rir_bank(rirs)
+        batch = r.prepare([AudioRequest(rir=i, source=s4, offset=3 * sr) for i in ids])
+
+        def c4(i):
+            r.set_dense_rir_bank(r.sh_decode(amb, az))
+            r.execute(batch, out=out)
+        run("C4_decode_conv", c4, B4, 36 * L + 8 * 65 * 26, 44e6,
+            "256 envs: 9-channel ambisonic RIR (48000 taps) -> SH rotate + HRTF decode -> valid-mode convolution -> (65,26,2)")
+        del r, amb
+    except Exception as e:          # noqa: BLE001
+        res["C4_error"] = repr(e)[:200]
+    try:
+        res["C5_rollout"] = c5_rollout(dev, torch)
+    except Exception as e:          # noqa: BLE001
+        res["C5_error"] = repr(e)[:200]
+    return res
+
+
+def c5_rollout(dev, torch, n_envs=16, num_steps=150, sr=16000, taps=16000):
+    """BASELINE.json configs[4]: DD-PPO rollout, 16 envs per GPU, audio observation fused into the step (trace-replay
+    env): env-steps/s with the env_time / pth_time split of ppo_trainer.py:125-194."""
+    from soundspaces_b200.replay import AudioPolicy, ReplayScene, ReplaySim, ReplayVectorEnv, collect_rollout
+    from soundspaces_b200.simulator import AudioRenderService
+    from synth import make_rir, make_source
+    svc = AudioRenderService(sr, device=dev, max_taps=taps, n_terms=1)
+    scene = ReplayScene("apartment_replay", side=8)
+    rng = np.random.default_rng(11)
+    base = np.stack([make_rir(500 + i, taps) for i in range(8)])
+    mix = rng.standard_normal((4, scene.n_nodes, 8)).astype(np.float32) / 3.0
+    rirs = np.einsum("anb,ble->anle", mix, base).astype(np.float32)          # [azimuth][node](taps, 2)
+    scene.register_rirs(svc, source=0, rirs=rirs)
+    clip = make_source(21, sr)
+    sims = [ReplaySim(svc, scene, "telephone.wav", clip, source_node=0, start_node=int(rng.integers(scene.n_nodes)),
+                      start_rotation=int(rng.integers(4)) * 90) for _ in range(n_envs)]
+    envs = ReplayVectorEnv(sims)
+    policy = AudioPolicy(svc.renderer.spec_shape).to(dev)
+    storage = torch.zeros((num_steps + 1, n_envs) + svc.renderer.spec_shape, device=dev)
+    trace = rng.choice([1, 1, 1, 2, 3], size=(num_steps, n_envs))              # recorded action trace (no STOP)
+    collect_rollout(envs, policy, storage, 20, trace[:20])                     # warm-up
+    l0, f0 = svc.renderer.ctx.launch_count, svc.batcher.flushes
+    t0 = time.time()
+    pth, env_t, n = collect_rollout(envs, policy, storage, num_steps, trace)
+    wall = time.time() - t0
+    rendered = sum(len(s._spectrogram_cache) for s in sims)
+    return {"value": n / wall, "unit": "env-steps/s", "envs": n_envs, "num_steps": num_steps, "env_time_s": env_t, "pth_time_s": pth,
+            "wall_s": wall, "renders": svc.batcher.flushes - f0, "kernel_launches": svc.renderer.ctx.launch_count - l0,
+            "memo_entries": rendered, "rir_miss_rate": svc.miss_rate,
+            "workload": "trace-replay env (8x8 grid scene, 16 kHz, 16000-tap RIRs resident) x SpectrogramSensor (deferred) x batch_obs into "
+                        "rollouts.observations['spectrogram'][step+1] x AudioCNN-shaped policy; ONE render per step for all envs"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -452,11 +774,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=0)
     ap.add_argument("--conv-mode", type=int, default=0, help="0: mac_bins + ifft kernels, 1: fused mac_ifft")
+    ap.add_argument("--plan", default="partitioned", choices=["partitioned", "block64"],
+                    help="convolution plan of the headline leg: partitioned overlap-save (fastest) or the single-block cluster kernel (least traffic)")
     ap.add_argument("--chunks", type=int, default=2, help="pipeline depth of the host-buffer (e2e) entry")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--gather", action="store_true",
-                    help="N > 1: also time the centralised-policy mode (one in-place all-gather of the observations per step)")
+    ap.add_argument("--gather", action="store_true", help="(default for N > 1; kept for old command lines)")
+    ap.add_argument("--no-gather", action="store_true",
+                    help="N > 1: skip the centralised-policy leg (one in-place all-gather of the observations per step)")
     ap.add_argument("--cpu-frames-per-core", type=int, default=150)
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the other BASELINE configs (extra_workloads)")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind ranks to their GPU's NUMA node")
+    ap.add_argument("--miss-rate", type=float, default=0.10, help="e2e_resident_bank: fraction of envs whose RIR is uploaded per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -85,14 +85,21 @@ typedef struct {
     uint32_t flags;        /* SSB_FLAG_* */
 } ssb_req;
 
+/* Two convolution plans:
+ *  - partitioned overlap-save (log2n 12, 13 or 14): any RIR length, one or two terms; three kernels with the RIR
+ *    spectra and the partition sums as L2-visible intermediates;
+ *  - single block (log2n 16): ONE 65536-point circular convolution per env by a 4-CTA cluster, RIR FFT x source
+ *    spectrum x inverse FFT fused in one kernel (no intermediate but the waveform); one term, RIRs of at most
+ *    65536 - sr + 1 effective taps.  The source enters as ONE 65536-point spectrum per (clip, offset):
+ *    ssb_source_windows with nw = 1, wofs = 0 writes 65536 float2; x_nw / x_wofs of the request are ignored. */
 typedef struct {
-    int32_t log2n;      /* FFT size of the overlap-save blocks: 12, 13 or 14 */
-    int32_t block;      /* P = 2^log2n / 2 output samples per block */
+    int32_t log2n;      /* 12, 13, 14: FFT size of the overlap-save blocks; 16: single-block plan */
+    int32_t block;      /* P = 2^log2n / 2 output samples per block (log2n 16: the shift D = 65536 - sr) */
     int32_t sr;         /* samples per output row (RIR_SAMPLING_RATE) */
-    int32_t n_blocks;   /* ceil(sr / P) */
-    int32_t max_parts;  /* RIR partitions the scratch is sized for */
-    int32_t n_terms;    /* 1 or 2 */
-    int64_t h_elems_per_env; /* float2 elements of RIR-spectrum scratch per env */
+    int32_t n_blocks;   /* ceil(sr / P) (log2n 16: 1) */
+    int32_t max_parts;  /* RIR partitions the scratch is sized for (log2n 16: 1) */
+    int32_t n_terms;    /* 1 or 2 (log2n 16: 1) */
+    int64_t h_elems_per_env; /* float2 elements of RIR-spectrum scratch per env (log2n 16: 0, d_hscratch unused) */
 } ssb_plan;
 
 int ssb_version(void);
@@ -110,7 +117,8 @@ int64_t ssb_launch_count(const ssb_ctx* ctx);
 #define SSB_K_SPECTROGRAM 2
 #define SSB_K_FWD_SRC 3
 #define SSB_K_MAC_BINS 4
-#define SSB_N_KERNELS 5
+#define SSB_K_CONV64K 5
+#define SSB_N_KERNELS 6
 int ssb_set_kernel_timing(ssb_ctx* ctx, int enable);
 int ssb_get_kernel_timing(ssb_ctx* ctx, double* ms_sum /*[SSB_N_KERNELS]*/, int64_t* counts /*[SSB_N_KERNELS]*/);
 
@@ -130,7 +138,8 @@ int ssb_set_chunks(ssb_ctx* ctx, int n);
  * waveform loads of the spectrogram kernel, 8 skip its FFT, 32 force the direct-form SH decode).  Results are wrong when non-zero. */
 int ssb_set_debug(ssb_ctx* ctx, int flags);
 
-/* Fill a plan.  log2n = 0 picks the default (12; 13 when max_taps > 24576). */
+/* Fill a plan.  log2n = 0 picks the partitioned default (12; 13 when max_taps > 24576); log2n = 16 asks for the
+ * single-block plan and fails with SSB_E_INVALID_ARG when n_terms != 1, sr > 61440 or max_taps > 65536 - sr + 1. */
 int ssb_make_plan(ssb_ctx* ctx, int sr, int max_taps, int n_terms, int log2n, ssb_plan* plan);
 
 /* spectrogram geometry: frames = 1 + sr/160, cols = ceil(frames/4) */

@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("SSB200_LIB", os.path.join(_HERE, "libssb200.so"))   # override: A/B builds while tuning
 SOURCES = [os.path.join(_HERE, "csrc", "ssb200.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "fft16.cuh"), os.path.join(ROOT, "include", "ssb200.h")]
+HEADERS = [os.path.join(_HERE, "csrc", "fft16.cuh"), os.path.join(_HERE, "csrc", "conv64k.cuh"),
+           os.path.join(ROOT, "include", "ssb200.h")]
 
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-O3", "-std=c++17"]
@@ -137,15 +138,16 @@ class Context:
         self.check(self.lib.ssb_make_plan(self.handle, sr, max_taps, n_terms, log2n, C.byref(plan)), "ssb_make_plan")
         return plan
 
-    KERNEL_NAMES = ("fwd_rir_kernel", "mac_ifft_kernel", "spectrogram_kernel", "fwd_src_kernel", "mac_bins_kernel")
+    KERNEL_NAMES = ("fwd_rir_kernel", "mac_ifft_kernel", "spectrogram_kernel", "fwd_src_kernel", "mac_bins_kernel",
+                    "conv64k_kernel")
 
     def set_kernel_timing(self, enable):
         self.check(self.lib.ssb_set_kernel_timing(self.handle, int(bool(enable))), "ssb_set_kernel_timing")
 
     def get_kernel_timing(self):
         """{kernel: (summed ms, launches)} since the last call (synchronises)."""
-        ms = (C.c_double * 5)()
-        cnt = (C.c_int64 * 5)()
+        ms = (C.c_double * len(self.KERNEL_NAMES))()
+        cnt = (C.c_int64 * len(self.KERNEL_NAMES))()
         self.check(self.lib.ssb_get_kernel_timing(self.handle, ms, cnt), "ssb_get_kernel_timing")
         return {n: (ms[i], cnt[i]) for i, n in enumerate(self.KERNEL_NAMES)}
 

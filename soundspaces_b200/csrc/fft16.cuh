@@ -252,6 +252,12 @@ __device__ __forceinline__ void group_barrier() {
     else __syncthreads();                                  // G > 32 only occurs with group == CTA (or 2 warps of it)
 }
 
+// barrier among the threads of one transform when they span more than a warp: the whole CTA by default; kernels
+// that run several transforms side by side in one CTA pass a named barrier of their group (conv64k.cuh)
+struct CtaBar {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
 // Forward transform.  In: v[q] = x[t + q*T].  Out: v[i] = spectrum slot (t, i).
 // w0: pass-0 twiddles of this thread (load_tw6 at column t of the pass-0 table), loaded by the
 //     caller so the loads can be issued early.
@@ -260,22 +266,22 @@ __device__ __forceinline__ void group_barrier() {
 // LANE_STAGE = false leaves out the final radix-M stage across lanes: the caller folds it into its own
 // reads (the STFT kernel does, for M = 2: lane 2a then holds P_a[i], lane 2a+1 holds Q_a[i], and
 // X[a + 16 i] = P + Q, X[a + 16 i + N/2] = P - Q).
-template <int LOG2N, bool LANE_STAGE = true>
+template <int LOG2N, bool LANE_STAGE = true, class Bar = CtaBar>
 __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __restrict__ buf, const Tw6& w0,
-                                            const float2* __restrict__ stw) {
+                                            const float2* __restrict__ stw, const Bar bar = Bar()) {
     using P = FftPlan<LOG2N>;
     fft16<false, true>(v, w0);
 #pragma unroll
     for (int p = 1; p < P::NPASS; ++p) {
         const int st = P::stride(p), stp = P::stride(p - 1);
         // exchange: written with pass p-1 layout, read with pass p layout; shared by stp threads
-        if (p > 1) { if (stp <= 32) __syncwarp(); else __syncthreads(); }      // previous readers of this region
+        if (p > 1) { if (stp <= 32) __syncwarp(); else bar(); }      // previous readers of this region
         {
             float2* __restrict__ wp = buf + pass_base<P::PADST>(t, stp);
 #pragma unroll
             for (int i = 0; i < 16; ++i) wp[i * pass_stride<P::PADST>(P::stride(p - 1))] = v[i];
         }
-        if (stp <= 32) __syncwarp(); else __syncthreads();
+        if (stp <= 32) __syncwarp(); else bar();
         {
             const float2* __restrict__ rp = buf + pass_base<P::PADST>(t, st);
 #pragma unroll
@@ -315,9 +321,10 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], int t, float2* __re
 // Inverse transform (unscaled).  In: v[i] = spectrum slot (t, i).  Out: v[q] = N * x[t + q*T].
 // gtw0: pass-0 table (column 0; global memory when TW0_GLOBAL); its six entries are fetched before
 // the last exchange so the latency overlaps it.  stw: as for fft_forward.
-template <int LOG2N, bool TW0_GLOBAL = true>
+template <int LOG2N, bool TW0_GLOBAL = true, class Bar = CtaBar>
 __device__ __forceinline__ void fft_inverse(float2 (&v)[16], int t, float2* __restrict__ buf,
-                                            const float2* __restrict__ gtw0, const float2* __restrict__ stw) {
+                                            const float2* __restrict__ gtw0, const float2* __restrict__ stw,
+                                            const Bar bar = Bar()) {
     using P = FftPlan<LOG2N>;
     if constexpr (P::M == 2) {
         const float sgn = (t & 1) ? -1.f : 1.f;                // lower lane: v + o, upper lane: o - v  (one FFMA each)
@@ -352,13 +359,13 @@ __device__ __forceinline__ void fft_inverse(float2 (&v)[16], int t, float2* __re
         if (p == 1) w0 = load_tw6<TW0_GLOBAL>(gtw0, P::stride(0), t);      // in flight during the exchange
         // exchange: written with pass p layout, read with pass p-1 layout; shared by stn threads.
         // The region was last read (previous exchange) by this thread's st-group only.
-        if (p < P::NPASS - 1) { if (st <= 32) __syncwarp(); else __syncthreads(); }
+        if (p < P::NPASS - 1) { if (st <= 32) __syncwarp(); else bar(); }
         {
             float2* __restrict__ wp = buf + pass_base<P::PADST>(t, st);
 #pragma unroll
             for (int i = 0; i < 16; ++i) wp[i * pass_stride<P::PADST>(P::stride(p))] = v[i];
         }
-        if (stn <= 32) __syncwarp(); else __syncthreads();
+        if (stn <= 32) __syncwarp(); else bar();
         {
             const float2* __restrict__ rp = buf + pass_base<P::PADST>(t, stn);
 #pragma unroll

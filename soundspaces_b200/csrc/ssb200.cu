@@ -19,6 +19,7 @@
 
 #include "../../include/ssb200.h"
 #include "fft16.cuh"
+#include "conv64k.cuh"
 
 using namespace ssb;
 
@@ -44,7 +45,7 @@ using namespace ssb;
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
-enum { K_FWD_RIR = 0, K_MAC_IFFT = 1, K_SPECTROGRAM = 2, K_FWD_SRC = 3, K_MAC_BINS = 4, K_COUNT = SSB_N_KERNELS };
+enum { K_FWD_RIR = 0, K_MAC_IFFT = 1, K_SPECTROGRAM = 2, K_FWD_SRC = 3, K_MAC_BINS = 4, K_CONV64K = 5, K_COUNT = SSB_N_KERNELS };
 #define SSB_MAX_CHUNKS 32
 #define SSB_MAX_STREAMS 8
 struct TimedLaunch { int kernel; cudaEvent_t a, b; };
@@ -53,6 +54,7 @@ struct ssb_ctx {
     int device;
     int sm_count;
     float2* tw[16];      // twiddle tables by log2n (device)
+    float2* twm64;       // single-block plan: TWM[r][tau] = w_65536^(tau r), r < 16, tau < 1024
     float* window;       // 512-float centre-padded periodic Hann(400)
     int64_t launches;
     // optional per-kernel CUDA-event timing (bench.py roofline); see ssb_set_kernel_timing
@@ -96,7 +98,7 @@ struct ssb_ctx {
                      "%s failed: %s", #call, cudaGetErrorString(e__));                  \
     } while (0)
 
-static const int kSupportedLog2[] = {9, 12, 13, 14};
+static const int kSupportedLog2[] = {9, 12, 13, 14, 16};
 
 // Every ABI entry runs on the context's device, whatever the caller's current device is, and restores the
 // caller's device afterwards (one process may hold contexts on several devices: per-rank trainers do not, but
@@ -319,7 +321,7 @@ mac_bins_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ xpo
 // grid (B, n_blocks); block T.
 // ---------------------------------------------------------------------------
 #ifndef IFFT_TW_GLOBAL
-#define IFFT_TW_GLOBAL 0         // 0: twiddles of passes >= 1 staged in shared memory (measured default)
+#define IFFT_TW_GLOBAL 1         // 1: later-pass twiddles straight from the L1-resident global table (r02 A/B: mac_ifft 45.2 -> 41.9 us per step); 0: staged in shared memory
 #endif
 #ifndef IFFT12_MIN_BLOCKS
 #define IFFT12_MIN_BLOCKS 5      // resident CTAs per SM asked of ptxas for the N = 4096 instance
@@ -1041,6 +1043,23 @@ static int create_impl(ssb_ctx* ctx, int device) {
         SSB_CUDA(ctx, cudaMalloc(&ctx->window, sizeof(hw)));
         SSB_CUDA(ctx, cudaMemcpy(ctx->window, hw, sizeof(hw), cudaMemcpyHostToDevice));
     }
+    {   // single-block plan: w_64 constants (per-device constant memory), the [16][1024] modulation table, smem opt-in
+        float2 w64[64];
+        for (int k = 0; k < 64; ++k) {
+            const double a = -2.0 * M_PI * (double)k / 64.0;
+            w64[k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        SSB_CUDA(ctx, cudaMemcpyToSymbol(kW64, w64, sizeof(w64)));
+        std::vector<float2> twm(C64_TWM_ELEMS);
+        for (int r = 0; r < 16; ++r)
+            for (int tau = 0; tau < 1024; ++tau) {
+                const double a = -2.0 * M_PI * (double)((r * tau) % C64_M) / (double)C64_M;
+                twm[r * 1024 + tau] = make_float2((float)cos(a), (float)sin(a));
+            }
+        SSB_CUDA(ctx, cudaMalloc(&ctx->twm64, twm.size() * sizeof(float2)));
+        SSB_CUDA(ctx, cudaMemcpy(ctx->twm64, twm.data(), twm.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        SSB_CUDA(ctx, cudaFuncSetAttribute(conv64k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C64_SMEM_BYTES));
+    }
     if (setup_smem_attrs<12>() || setup_smem_attrs<13>() || setup_smem_attrs<14>())
         SSB_FAIL(ctx, SSB_E_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s",
                  cudaGetErrorString(cudaGetLastError()));
@@ -1053,6 +1072,7 @@ extern "C" void ssb_destroy(ssb_ctx* ctx) {
     for (int l = 0; l < 16; ++l)
         if (ctx->tw[l]) cudaFree(ctx->tw[l]);
     if (ctx->window) cudaFree(ctx->window);
+    if (ctx->twm64) cudaFree(ctx->twm64);
     if (ctx->yscratch) cudaFree(ctx->yscratch);
     if (ctx->gscratch) cudaFree(ctx->gscratch);
     if (ctx->s_comp[0]) {
@@ -1138,7 +1158,21 @@ extern "C" int ssb_make_plan(ssb_ctx* ctx, int sr, int max_taps, int n_terms, in
     // default block size: N = 4096 keeps 4 CTAs per SM and the finest tiling; beyond ~12 partitions the per-bin
     // partition sums dominate and N = 8192 is the better plan (measured at config 3)
     if (log2n == 0) log2n = max_taps > 24576 ? 13 : 12;
-    if (log2n < 12 || !log2_supported(log2n)) SSB_FAIL(ctx, SSB_E_INVALID_ARG, "log2n %d unsupported (12, 13, 14)", log2n);
+    if (log2n == C64_LOG2M) {
+        // single-block plan: out[m] sits at circular index m + D, D = 65536 - sr; alias-free for taps <= D + 1
+        if (n_terms != 1 || sr < SSB_N_FFT || sr > C64_M - C64_NS || max_taps < 0 || max_taps > C64_M - sr + 1)
+            SSB_FAIL(ctx, SSB_E_INVALID_ARG, "single-block plan needs n_terms = 1, sr <= %d and max_taps <= 65536 - sr + 1 "
+                     "(sr=%d max_taps=%d n_terms=%d)", C64_M - C64_NS, sr, max_taps, n_terms);
+        plan->log2n = C64_LOG2M;
+        plan->block = C64_M - sr;
+        plan->sr = sr;
+        plan->n_blocks = 1;
+        plan->max_parts = 1;
+        plan->n_terms = 1;
+        plan->h_elems_per_env = 0;
+        return SSB_OK;
+    }
+    if (log2n < 12 || !log2_supported(log2n)) SSB_FAIL(ctx, SSB_E_INVALID_ARG, "log2n %d unsupported (12, 13, 14, 16)", log2n);
     if (sr < SSB_N_FFT || max_taps < 0 || n_terms < 1 || n_terms > 2)
         SSB_FAIL(ctx, SSB_E_INVALID_ARG, "bad plan arguments sr=%d max_taps=%d n_terms=%d", sr, max_taps, n_terms);
     const int P = (1 << log2n) / 2;
@@ -1154,6 +1188,12 @@ extern "C" int ssb_make_plan(ssb_ctx* ctx, int sr, int max_taps, int n_terms, in
 
 static int check_plan(ssb_ctx* ctx, const ssb_plan* plan) {
     if (!ctx) return SSB_E_INVALID_ARG;
+    if (plan && plan->log2n == C64_LOG2M) {
+        if (plan->n_terms != 1 || plan->max_parts != 1 || plan->n_blocks != 1 || plan->sr < SSB_N_FFT ||
+            plan->sr > C64_M - C64_NS || plan->block != C64_M - plan->sr)
+            SSB_FAIL(ctx, SSB_E_INVALID_ARG, "invalid single-block plan");
+        return SSB_OK;
+    }
     if (!plan || plan->log2n < 12 || !log2_supported(plan->log2n) || plan->block != (1 << plan->log2n) / 2 ||
         plan->n_terms < 1 || plan->n_terms > 2 || plan->max_parts < 1 ||
         plan->n_blocks != (plan->sr + plan->block - 1) / plan->block)
@@ -1180,6 +1220,16 @@ static int ssb_source_windows_impl(ssb_ctx* ctx, const ssb_plan* plan, const flo
         SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_source_windows: bad arguments (S=%d nw=%d wofs=%d)", S, nw, wofs);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
+    if (plan->log2n == C64_LOG2M) {
+        if (nw != 1 || wofs != 0) SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_source_windows: the single-block plan has one spectrum (nw = 1, wofs = 0)");
+        {
+            LaunchTimer lt(ctx, K_FWD_SRC, st);
+            src64k_kernel<<<16, 256, C64_BUF * sizeof(float2), st>>>(d_src, S, (long long)m0, wrap, plan->block, (float2*)d_x,
+                                                                    ctx->tw[12], ctx->twm64);
+        }
+        SSB_CUDA(ctx, cudaGetLastError());
+        return SSB_OK;
+    }
     switch (plan->log2n) {
         case 12: e = launch_src<12>(ctx, d_src, S, m0, wrap, nw, wofs, (float2*)d_x, st); break;
         case 13: e = launch_src<13>(ctx, d_src, S, m0, wrap, nw, wofs, (float2*)d_x, st); break;
@@ -1228,7 +1278,7 @@ static cudaError_t launch_conv_sub(ssb_ctx* ctx, const ssb_plan* plan, int B, co
 
 // partition-sum scratch Y[B][n_blocks][N] (mode 0), owned by the context
 static cudaError_t ensure_yscratch(ssb_ctx* ctx, const ssb_plan* plan, int B, cudaStream_t st) {
-    if (ctx->conv_mode != 0) return cudaSuccess;
+    if (ctx->conv_mode != 0 || plan->log2n == C64_LOG2M) return cudaSuccess;
     const size_t need = (size_t)B * plan->n_blocks * ((size_t)1 << plan->log2n);
     if (need <= ctx->yscratch_elems) return cudaSuccess;
     if (ctx->yscratch) {
@@ -1246,6 +1296,12 @@ static cudaError_t ensure_yscratch(ssb_ctx* ctx, const ssb_plan* plan, int B, cu
 static cudaError_t launch_conv_any(ssb_ctx* ctx, const ssb_plan* plan, int B, const ssb_req* d_reqs, const float* d_rir_bank,
                                    const void* d_xpool, void* d_h, float2* y, float* d_wave, int64_t wave_stride,
                                    cudaStream_t st) {
+    if (plan->log2n == C64_LOG2M) {
+        LaunchTimer lt(ctx, K_CONV64K, st);
+        conv64k_kernel<<<C64_CL * B, C64_TPB, C64_SMEM_BYTES, st>>>(d_reqs, (const float2*)d_rir_bank, (const float2*)d_xpool,
+                                                                     d_wave, (long long)wave_stride, plan->sr, ctx->tw[12], ctx->twm64);
+        return cudaGetLastError();
+    }
     switch (plan->log2n) {
         case 12: return launch_conv_sub<12>(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_h, y, d_wave, wave_stride, st);
         case 13: return launch_conv_sub<13>(ctx, plan, B, d_reqs, d_rir_bank, d_xpool, d_h, y, d_wave, wave_stride, st);
@@ -1259,7 +1315,7 @@ static int ssb_convolve_batch_impl(ssb_ctx* ctx, const ssb_plan* plan, int B, co
     int rc = check_plan(ctx, plan);
     if (rc) return rc;
     if (B == 0) return SSB_OK;
-    if (B < 0 || B > 65535 || !d_reqs || !d_rir_bank || !d_xpool || !d_hscratch || !d_wave || wave_stride < plan->sr)
+    if (B < 0 || B > 16383 * 4 || !d_reqs || !d_rir_bank || !d_xpool || (!d_hscratch && plan->h_elems_per_env) || !d_wave || wave_stride < plan->sr)
         SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_convolve_batch: bad arguments (B=%d wave_stride=%lld sr=%d)", B,
                  (long long)wave_stride, plan->sr);
     if (((uintptr_t)d_rir_bank & 7) || ((uintptr_t)d_xpool & 7) || ((uintptr_t)d_hscratch & 7))
@@ -1334,7 +1390,7 @@ static int ssb_render_batch_impl(ssb_ctx* ctx, const ssb_plan* plan, int B, cons
     }
     int rc = check_plan(ctx, plan);
     if (rc) return rc;
-    if (B > 65535 || !d_reqs || !d_rir_bank || !d_xpool || !d_hscratch || !d_wave || !d_spec || wave_stride < plan->sr)
+    if (B > 65535 || !d_reqs || !d_rir_bank || !d_xpool || (!d_hscratch && plan->h_elems_per_env) || !d_wave || !d_spec || wave_stride < plan->sr)
         SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_render_batch: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     if (!ctx->s_comp[0]) {

@@ -14,6 +14,27 @@ import torch.distributed as dist
 from .planning import shard_envs  # noqa: F401
 
 
+def gpu_numa_cpus(device_index: int):
+    """(NUMA node, CPU list) of the host socket a GPU hangs off, from sysfs
+    (``/sys/bus/pci/devices/<domain:bus:dev.fn>/numa_node`` and ``/sys/devices/system/node/node<N>/cpulist``), or
+    ``(None, [])`` when the box does not expose it.  Eight ranks each pushing their RIRs through pinned buffers that
+    live on the wrong socket share one inter-socket link: binding rank -> local CPUs before the pinned buffers are
+    allocated (first touch) keeps every rank's host traffic on its own socket."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None, []
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        return node, cpus
+    except Exception:          # noqa: BLE001 - containers often hide sysfs
+        return None, []
+
+
 def gather_observations(local: torch.Tensor, n_envs: int, rank: int, world: int) -> torch.Tensor:
     """All-gather the per-rank rows (rank r holds envs r, r+G, r+2G, ...) into the
     (n_envs, ...) batch in env order.  Ragged shards are padded to the largest shard."""

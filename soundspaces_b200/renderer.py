@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -64,6 +65,7 @@ class PreparedBatch:
     n: int
     reqs_host: np.ndarray
     reqs_dev: torch.Tensor
+    plan: object = None            # the ssb_plan the requests were resolved for (partitioned or single-block)
 
 
 def _dev_index(device):
@@ -121,7 +123,7 @@ class WaveformOps:
 
 class BatchedAudioRenderer:
     def __init__(self, sr: int, max_taps: int, device="cuda:0", n_terms: int = 1, log2n: int = 0,
-                 pad_mode: str = "reflect", xpool_bytes: int = 512 << 20):
+                 pad_mode: str = "reflect", xpool_bytes: int = 512 << 20, prefer_block64: Optional[bool] = None):
         self.sr = int(sr)
         self.device = torch.device("cuda", _dev_index(device))
         self.pad_mode = PAD_MODES[pad_mode]
@@ -131,7 +133,22 @@ class BatchedAudioRenderer:
         self.ctx = _lib.Context(self.device.index)
         self.lib = self.ctx.lib
         self.max_taps = int(max_taps)
-        self.plan = self.ctx.make_plan(self.sr, self.max_taps, n_terms, log2n)
+        # Two plans (include/ssb200.h).  The partitioned overlap-save plan handles every request and is the FASTER one
+        # on B200 (config 2: 0.091 ms per 128-env step); the single-block plan (one fused 65536-point cluster kernel per
+        # env, no H / Y intermediates: 33 MB of DRAM traffic per step instead of 180 MB) is the LOW-TRAFFIC one
+        # (0.118 ms) and serves batches whose requests all have one term and at most 65536 - sr + 1 effective taps.
+        # prefer_block64=True (or SSB200_BLOCK64=1) takes it whenever a batch is eligible -- chosen per batch in
+        # _prepare_columns; log2n = 16 forces it (requests that do not fit raise).  DESIGN.md section 4 has the numbers.
+        self.plan64 = None
+        self.block64_taps = 65536 - self.sr + 1
+        if prefer_block64 is None:
+            prefer_block64 = os.environ.get("SSB200_BLOCK64", "0") == "1"
+        if (log2n == 16 or (log2n == 0 and prefer_block64)) and self.sr <= 65536 - 4096:
+            self.plan64 = self.ctx.make_plan(self.sr, min(self.max_taps, self.block64_taps), 1, 16)
+        self.force_block64 = log2n == 16
+        if self.force_block64 and (self.plan64 is None or self.max_taps > self.block64_taps or n_terms != 1):
+            raise ValueError(f"log2n=16 (single-block plan) needs n_terms=1 and max_taps <= {self.block64_taps} at sr={self.sr}")
+        self.plan = self.ctx.make_plan(self.sr, self.max_taps, n_terms, 0 if log2n == 16 else log2n)
         self.N = 1 << self.plan.log2n
         self.P = self.plan.block
         self.spec_shape = spectrogram_shape(self.sr)
@@ -146,7 +163,7 @@ class BatchedAudioRenderer:
         self._sources: list[torch.Tensor] = []
         # window-spectra pool: allocated on first use (a renderer that only runs the STFT / intensity kernels on
         # waveforms it is handed -- SpectrogramSensor.compute_spectrogram on a host array -- never needs it)
-        self._xpool_elems = max(xpool_bytes // 8, 64 * self.N)      # float2 elements
+        self._xpool_elems = max(xpool_bytes // 8, 64 * self.N, 8 * 65536 if self.plan64 is not None else 0)   # float2 elements
         self._xpool_t = None
         self._xpool_used = 0                  # float2 elements
         self._xcache: dict = {}
@@ -333,14 +350,20 @@ class BatchedAudioRenderer:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _windows(self, source: int, offset: int, wrap: bool, out_samples: int):
-        """Cached overlap-save window spectra of (clip, offset).  Returns (x_offset, nw, wofs)."""
-        nblk, wofs, nw = window_layout(self.P, self.plan.max_parts, offset, out_samples)
-        key = (source, offset, bool(wrap), nblk, wofs)
+    def _windows(self, source: int, offset: int, wrap: bool, out_samples: int, block64: bool = False):
+        """Cached source spectra of (clip, offset): the overlap-save window set of the partitioned plan, or the one
+        65536-point spectrum of the single-block plan.  Returns (x_offset, nw, wofs)."""
+        if block64:
+            nblk, wofs, nw = 1, 0, 1
+            key = (source, offset, bool(wrap), "block64")
+            plan, need = self.plan64, 65536
+        else:
+            nblk, wofs, nw = window_layout(self.P, self.plan.max_parts, offset, out_samples)
+            key = (source, offset, bool(wrap), nblk, wofs)
+            plan, need = self.plan, nw * self.N
         hit = self._xcache.get(key)
         if hit is not None:
             return hit
-        need = nw * self.N
         if self._xpool_used + need > self._xpool.numel() // 2:
             if need > self._xpool.numel() // 2:
                 raise RuntimeError("window-spectra pool too small for one clip; raise xpool_bytes")
@@ -353,13 +376,13 @@ class BatchedAudioRenderer:
         x_off = self._xpool_used
         src = self._sources[source]
         self.ctx.check(self.lib.ssb_source_windows(
-            self.ctx.handle, C.byref(self.plan), src.data_ptr(), src.numel(), int(offset), int(bool(wrap)),
+            self.ctx.handle, C.byref(plan), src.data_ptr(), src.numel(), int(offset), int(bool(wrap)),
             nw, wofs, self._xpool.data_ptr() + 8 * x_off, self._stream()), "ssb_source_windows")
         self._xpool_used += need
         self._xcache[key] = (x_off, nw, wofs)
         return self._xcache[key]
 
-    def _fill_terms(self, terms, rows, rir_ids, sources, offsets, wraps, out_samples):
+    def _fill_terms(self, terms, rows, rir_ids, sources, offsets, wraps, out_samples, block64=False):
         """Vectorised fill of one convolution term for the requests ``rows`` (indices into the batch):
         bank offsets and effective tap counts by array indexing, one window-set lookup per distinct
         ``(source, offset, wrap, out_samples)`` instead of one per request."""
@@ -379,13 +402,13 @@ class BatchedAudioRenderer:
         rows, rir_ids, lens = rows[has], rir_ids[has], lens[has]
         sources, offsets, wraps, out_samples = sources[has], offsets[has], wraps[has], out_samples[has]
         taps = np.minimum(lens, offsets + out_samples)          # planning.effective_taps
-        too_long = taps > self.plan.max_parts * self.P
+        too_long = taps > (self.block64_taps if block64 else self.plan.max_parts * self.P)
         if too_long.any():
             k = int(np.argmax(too_long))
             raise ValueError(f"RIR {int(rir_ids[k])} needs {int(taps[k])} taps > max_taps={self.max_taps} the renderer was sized for")
         keys = np.stack([sources, offsets, wraps.astype(np.int64), out_samples], axis=1)
         if (keys == keys[0]).all():                             # the usual step: every env plays the same clip window
-            xs = np.asarray([self._windows(int(keys[0, 0]), int(keys[0, 1]), bool(keys[0, 2]), int(keys[0, 3]))], dtype=np.int64)
+            xs = np.asarray([self._windows(int(keys[0, 0]), int(keys[0, 1]), bool(keys[0, 2]), int(keys[0, 3]), block64)], dtype=np.int64)
             inverse = np.zeros(rows.size, dtype=np.int64)
         else:
             uniq, first, inverse = np.unique(keys, axis=0, return_index=True, return_inverse=True)
@@ -393,7 +416,7 @@ class BatchedAudioRenderer:
             xs = np.empty((uniq.shape[0], 3), dtype=np.int64)
             for u in np.argsort(first):                         # allocate window sets in request order
                 src, off, wrap, outs = (int(v) for v in uniq[u])
-                xs[u] = self._windows(src, off, bool(wrap), outs)
+                xs[u] = self._windows(src, off, bool(wrap), outs, block64)
         terms["rir_offset"][rows] = off_arr[rir_ids]
         terms["x_offset"][rows] = xs[inverse, 0]
         terms["rir_taps"][rows] = taps
@@ -457,8 +480,9 @@ class BatchedAudioRenderer:
             rows = np.flatnonzero(~silent)
             g = f[rows]
             terms = reqs["term"]
-            self._fill_terms(terms[:, 0], rows, g[:, 0], g[:, 1], g[:, 2], g[:, 3] != 0, g[:, 5])
             sel = g[:, 7] >= 0
+            block64 = self._block64_eligible(g, sel)
+            self._fill_terms(terms[:, 0], rows, g[:, 0], g[:, 1], g[:, 2], g[:, 3] != 0, g[:, 5], block64)
             if sel.any():
                 if self.plan.n_terms < 2:
                     raise ValueError("renderer was created with n_terms=1; distractors need n_terms=2")
@@ -466,13 +490,34 @@ class BatchedAudioRenderer:
                 d = g[sel]
                 k = d.shape[0]
                 self._fill_terms(terms[:, 1], rows[sel], d[:, 6], d[:, 7], np.zeros(k, np.int64), np.zeros(k, bool), d[:, 5])
+        else:
+            block64 = self.plan64 is not None
         dev = torch.from_numpy(reqs.view(np.uint8).reshape(-1)).to(self.device, non_blocking=False)
-        return PreparedBatch(n, reqs, dev)
+        return PreparedBatch(n, reqs, dev, self.plan64 if block64 else self.plan)
 
-    def _scratch(self, n):
-        h_elems = n * self.plan.h_elems_per_env
+    def _block64_eligible(self, g: np.ndarray, has_distractor: np.ndarray) -> bool:
+        """Single-block plan for this batch?  Every non-silent request must have one term and at most
+        65536 - sr + 1 EFFECTIVE taps (min(file taps, offset + out_samples), planning.effective_taps)."""
+        if self.plan64 is None:
+            return False
+        ok = not has_distractor.any()
+        if ok and g.shape[0]:
+            if self._bank_index is None:
+                self._bank_index = (np.asarray(self._rir_off, dtype=np.int64), np.asarray(self._rir_len, dtype=np.int64))
+            len_arr = self._bank_index[1]
+            ids = g[:, 0]
+            if ids.size and int(ids.max()) >= len(len_arr):
+                raise ValueError(f"unknown RIR id {int(ids.max())}")
+            lens = np.where(ids >= 0, len_arr[np.where(ids >= 0, ids, 0)] if len(len_arr) else 0, 0)
+            ok = bool((np.minimum(lens, g[:, 2] + g[:, 5]) <= self.block64_taps).all())
+        if self.force_block64 and not ok:
+            raise ValueError(f"log2n=16: a request has a distractor or more than {self.block64_taps} effective taps")
+        return ok
+
+    def _scratch(self, n, plan=None):
+        h_elems = n * (self.plan if plan is None else plan).h_elems_per_env
         if self._hscratch is None or self._hscratch.numel() < 2 * h_elems:
-            self._hscratch = torch.empty(2 * h_elems, dtype=torch.float32, device=self.device)
+            self._hscratch = torch.empty(max(2 * h_elems, 2), dtype=torch.float32, device=self.device)
         if self._wave is None or self._wave.shape[0] < n:
             self._wave = torch.empty((n, 2, self.sr), dtype=torch.float32, device=self.device)
         return self._hscratch, self._wave[:n]
@@ -496,9 +541,9 @@ class BatchedAudioRenderer:
             return (spec, self._scratch(0)[1]) if want_wave else spec
         if not (spec.is_cuda and spec.is_contiguous() and tuple(spec.shape) == shape and spec.dtype == torch.float32):
             raise ValueError("bad output tensor")
-        hs, wave = self._scratch(n)
+        hs, wave = self._scratch(n, batch.plan)
         self.ctx.check(self.lib.ssb_render_batch(
-            self.ctx.handle, C.byref(self.plan), n, batch.reqs_dev.data_ptr(), self._bank.data_ptr(),
+            self.ctx.handle, C.byref(batch.plan), n, batch.reqs_dev.data_ptr(), self._bank.data_ptr(),
             self._xpool.data_ptr(), hs.data_ptr(), wave.data_ptr(), self.sr,
             self.pad_mode | (0x100 if channels_first else 0), spec.data_ptr(), self._stream()), "ssb_render_batch")
         return (spec, wave) if want_wave else spec
@@ -550,17 +595,20 @@ class BatchedAudioRenderer:
         with self._inline_rirs(requests):
             return self.execute(self.prepare(requests), want_wave=want_wave)
 
+    def convolve_prepared(self, batch: PreparedBatch) -> torch.Tensor:
+        """Waveforms (n, 2, sr) of a prepared batch (renderer-owned buffer, overwritten by the next call)."""
+        hs, wave = self._scratch(batch.n, batch.plan)
+        if batch.n:
+            self.ctx.check(self.lib.ssb_convolve_batch(
+                self.ctx.handle, C.byref(batch.plan), batch.n, batch.reqs_dev.data_ptr(), self._bank.data_ptr(),
+                self._xpool.data_ptr(), hs.data_ptr(), wave.data_ptr(), self.sr, self._stream()),
+                "ssb_convolve_batch")
+        return wave
+
     def convolve(self, requests: Sequence[AudioRequest]) -> torch.Tensor:
         """Waveforms only: (n, 2, sr) -- ``get_current_audiogoal_observation`` for a batch."""
         with self._inline_rirs(requests):
-            batch = self.prepare(requests)
-            hs, wave = self._scratch(batch.n)
-            if batch.n:
-                self.ctx.check(self.lib.ssb_convolve_batch(
-                    self.ctx.handle, C.byref(self.plan), batch.n, batch.reqs_dev.data_ptr(), self._bank.data_ptr(),
-                    self._xpool.data_ptr(), hs.data_ptr(), wave.data_ptr(), self.sr, self._stream()),
-                    "ssb_convolve_batch")
-        return wave
+            return self.convolve_prepared(self.prepare(requests))
 
     def render_crossfade(self, cur: Sequence[AudioRequest], prev: Sequence[Optional[AudioRequest]],
                          want_wave: bool = False):
@@ -656,6 +704,9 @@ class HostSession:
         """All envs play ``source`` through their own RIR row (the 1-s clip branch)."""
         r = self.r
         reqs = np.zeros(self.n, dtype=REQ_DTYPE)
+        eff = np.minimum(self.taps if taps is None else np.asarray(taps), r.sr)
+        self.block64 = r.plan64 is not None and int(np.max(eff)) <= r.block64_taps
+        self.plan = r.plan64 if self.block64 else r.plan
         for i in range(self.n):
             reqs[i]["out_samples"] = r.sr
             if silent is not None and silent[i]:
@@ -664,9 +715,10 @@ class HostSession:
             L = self.taps if taps is None else int(taps[i])
             if L == 0:
                 continue
-            x_off, nw, wofs = r._windows(source, 0, False, r.sr)
+            x_off, nw, wofs = r._windows(source, 0, False, r.sr, self.block64)
             t = reqs[i]["term"][0]
-            t["rir_offset"], t["x_offset"], t["rir_taps"] = i * self.taps, x_off, min(L, r.sr, r.plan.max_parts * r.P)
+            t["rir_offset"], t["x_offset"] = i * self.taps, x_off
+            t["rir_taps"] = min(L, r.sr, r.block64_taps if self.block64 else r.plan.max_parts * r.P)
             t["x_nw"], t["x_wofs"] = nw, wofs
         self.h_reqs.numpy()[:] = reqs.view(np.uint8).reshape(-1)
 
@@ -674,11 +726,11 @@ class HostSession:
         """Enqueue H2D + kernels + D2H (asynchronous; the current stream completes when the results
         have landed in ``h_spec`` / ``h_wave``).  ``h_rir`` must not be refilled before that."""
         r = self.r
-        hs, wave = r._scratch(self.n)
+        hs, wave = r._scratch(self.n, self.plan)
         d_rir, d_reqs = self.d_rir[self._step & 1], self.d_reqs[self._step & 1]
         self._step += 1
         r.ctx.check(r.lib.ssb_render_batch_host(
-            r.ctx.handle, C.byref(r.plan), self.n, self.h_reqs.data_ptr(), self.h_rir.data_ptr(),
+            r.ctx.handle, C.byref(self.plan), self.n, self.h_reqs.data_ptr(), self.h_rir.data_ptr(),
             self.h_rir.numel() * 4, d_rir.data_ptr(), d_reqs.data_ptr(), r._xpool.data_ptr(),
             hs.data_ptr(), wave.data_ptr(), r.sr, r.pad_mode, self.d_spec.data_ptr(), self.h_spec.data_ptr(),
             self.h_wave.data_ptr() if self.h_wave is not None else None, self.n_chunks, r._stream()),

@@ -222,3 +222,155 @@ def test_rir_bank_budget_trim(tmp_path):
     for i in range(4):
         ref = ao.compute_audiogoal(src, rirs[i], sr)
         assert np.abs(outs[i] - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+# ----------------------------------------------------------------------------------------------
+# round 2: deferred handles behind the sensor API, batch_obs replacement, scene-safe memo, device Intensity
+# ----------------------------------------------------------------------------------------------
+def _fresh_service(sr, **kw):
+    from soundspaces_b200.simulator import AudioRenderService
+    return AudioRenderService(sr, **kw)
+
+
+def test_deferred_sensor_path_one_render_per_step(tmp_path):
+    """Per-env SpectrogramSensor.get_observation returns handles; batch_obs renders the whole step ONCE and hands
+    back the (N, 65, T', 2) CUDA view; values equal the oracle; memo hits launch nothing."""
+    from soundspaces_b200.batching import DeferredObservation
+    from soundspaces_b200.sensors import SpectrogramSensor, batch_obs
+    sr, n = 16000, 7
+    src = make_source(5, sr)
+    d = str(tmp_path)
+    rirs = [make_rir(40 + i, 2000 + 700 * i) for i in range(n)]
+    svc = _fresh_service(sr)
+    sims, sensors = [], []
+    for i in range(n):
+        write_rir(d, "replica", "apartment_0", 0, i, 1, sr, rirs[i])
+        sim = make_sim(d, sr, {"telephone.wav": src}, receiver=i, step_count=501 if i == 2 else 0)
+        sim.b200_deferred, sim._b200_svc = True, svc
+        sims.append(sim)
+        sensors.append(SpectrogramSensor(sim=sim, config=AttrDict()))
+    l0 = svc.renderer.ctx.launch_count
+    obs = [{"spectrogram": s.get_observation(observations={}, episode=None), "gps": np.float32([i, 0])}
+           for i, s in enumerate(sensors)]
+    assert all(isinstance(o["spectrogram"], DeferredObservation) and o["spectrogram"].pending for o in obs)
+    assert svc.renderer.ctx.launch_count == l0                       # nothing launched yet
+    batch = batch_obs(obs, device=svc.renderer.device)
+    spec = batch["spectrogram"]
+    assert spec.is_cuda and spec.shape == (n, 65, 26, 2) and svc.batcher.flushes == 1
+    assert spec.data_ptr() == svc.batcher.ring.data_ptr()            # a view of the ring: no stack, no copy
+    per_step = svc.renderer.ctx.launch_count - l0
+    for i in range(n):
+        ref = ao.compute_spectrogram(ao.compute_audiogoal(src, rirs[i], sr, silent=(i == 2)).astype(np.float32))
+        assert np.allclose(spec[i].cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
+    assert not spec[2].any()                                          # silence is exactly 0
+    # same positions again: all memo hits (the sims' own dicts), no kernels
+    l1 = svc.renderer.ctx.launch_count
+    obs2 = [{"spectrogram": s.get_observation(observations={}, episode=None)} for s in sensors]
+    assert all(o2["spectrogram"] is o["spectrogram"] for o, o2 in zip(obs, obs2))
+    assert torch.equal(batch_obs(obs2, device=svc.renderer.device)["spectrogram"], spec)
+    assert svc.renderer.ctx.launch_count == l1
+    # rendering straight into a rollout-storage slot (SURVEY N2)
+    for s in sims:
+        s._spectrogram_cache = dict()
+    slot = torch.zeros((n, 65, 26, 2), device=svc.renderer.device)
+    obs3 = [{"spectrogram": s.get_observation(observations={}, episode=None)} for s in sensors]
+    got = batch_obs(obs3, device=svc.renderer.device, out={"spectrogram": slot})["spectrogram"]
+    assert got.data_ptr() == slot.data_ptr() and torch.equal(slot, spec)
+    assert per_step <= 12                                             # one launch chain, not one per env
+    # host compat of a handle: the array the reference's sensor returns
+    assert np.allclose(np.asarray(obs3[1]["spectrogram"]), spec[1].cpu().numpy())
+
+
+def test_scene_change_with_equal_node_indices_is_not_a_memo_hit(tmp_path):
+    """ADVICE r1 (high) / VERDICT weak #2 on the real kernels: same (source, receiver, azimuth), other scene."""
+    from soundspaces_b200.sensors import VectorAudioObservations
+    sr, n = 16000, 3
+    src = make_source(6, sr)
+    d = str(tmp_path)
+    rirs = {s: [make_rir(seed + i, 3000 + 100 * i) for i in range(n)] for s, seed in (("apartment_0", 100), ("office_3", 200))}
+    for scene in rirs:
+        for i in range(n):
+            write_rir(d, "replica", scene, 0, i, 1, sr, rirs[scene][i])
+    Sim = make_sim_class()
+
+    class SceneSim(Sim):
+        scene = "apartment_0"
+
+        @property
+        def binaural_rir_dir(self):
+            return os.path.join(self.config.AUDIO.BINAURAL_RIR_DIR, self.config.SCENE_DATASET, self.scene)
+
+    sims = []
+    for i in range(n):
+        base = make_sim(d, sr, {"telephone.wav": src}, receiver=i)
+        sim = SceneSim()
+        sim.__dict__.update(base.__dict__)
+        sims.append(sim)
+    vec = VectorAudioObservations(sr)
+    a = vec.collect(sims).clone()
+    for s in sims:                                   # reconfigure() to another scene (simulator.py:395-397)
+        s.scene = "office_3"
+        s._audiogoal_cache, s._spectrogram_cache = dict(), dict()
+    b = vec.collect(sims).clone()
+    for i in range(n):
+        ra = ao.compute_spectrogram(ao.compute_audiogoal(src, rirs["apartment_0"][i], sr).astype(np.float32))
+        rb = ao.compute_spectrogram(ao.compute_audiogoal(src, rirs["office_3"][i], sr).astype(np.float32))
+        assert np.allclose(a[i].cpu().numpy(), ra, rtol=1e-4, atol=1e-5)
+        assert np.allclose(b[i].cpu().numpy(), rb, rtol=1e-4, atol=1e-5), "stale observation from the previous scene"
+
+
+def test_intensity_sensor_stays_on_device(tmp_path):
+    from soundspaces_b200.sensors import Intensity
+    sr = 16000
+    src, rir = make_source(8, sr), make_rir(8, 4000)
+    write_rir(str(tmp_path), "replica", "apartment_0", 0, 0, 1, sr, rir)
+    sim = make_sim(str(tmp_path), sr, {"telephone.wav": src})
+    sim._b200_svc = _fresh_service(sr)
+    val = Intensity(sim, AttrDict()).get_observation(observations={}, episode=None)
+    wave = ao.compute_audiogoal(src, rir, sr).astype(np.float32)
+    nonzero = (wave > 0.1 * wave.max()).argmax(axis=1).min()
+    ref = float(np.mean(wave[:, nonzero: nonzero + 150] ** 2))
+    assert isinstance(val, list) and abs(val[0] - ref) <= 1e-4 * ref
+    assert not sim._audiogoal_cache                   # the waveform never visited the host memo
+    w = sim.get_current_audiogoal_device()
+    assert w.is_cuda and sim.get_current_audiogoal_device() is w
+    sim._audiogoal_cache = dict()                     # scene / sound change resets the device memo too
+    assert sim.get_current_audiogoal_device() is not w
+
+
+def test_continuous_early_branch_does_not_wrap(golden):
+    """index < len(rir) and index + num_sample > len(clip): zeros past the clip end, not wrapped audio."""
+    from soundspaces_b200.simulator import B200ContinuousAudioMixin
+    sr = 16000
+    src = make_source(9, sr)[:15000].copy()           # short clip so that the window runs past its end
+    rir = make_rir(9, 14000)
+
+    class Sim(B200ContinuousAudioMixin):
+        @property
+        def current_source_sound(self):
+            return self._source_sound_dict[self._current_sound]
+
+    sim = Sim()
+    sim.config = AttrDict(STEP_TIME=0.25, AUDIO=AttrDict(RIR_SAMPLING_RATE=sr, CROSSFADE=False))
+    sim._episode_step_count, sim._duration = 0, 500
+    sim._current_sound, sim._source_sound_dict = "s", {"s": src}
+    sim._current_sample_index = 12000                 # 12000 - 14000 < 0: early branch; 12000 + 4000 > 15000
+    sim._prev_sim_obs = {"audio_sensor": np.asarray(rir).T.tolist()}
+    sim._last_rir = None
+    wave = sim.get_current_audiogoal_observation()
+    ref = ao.continuous_convolve_with_rir(src.astype(np.float64), rir.astype(np.float64), sr, 0.25, 12000)
+    check_wave(wave, ref)
+
+
+def test_render_on_second_renderer_leaves_current_device_alone():
+    """constructing / using a renderer must not switch the caller's current CUDA device."""
+    from soundspaces_b200 import AudioRequest, BatchedAudioRenderer
+    cur = torch.cuda.current_device()
+    r = BatchedAudioRenderer(16000, 4000, device=f"cuda:{torch.cuda.device_count() - 1}")
+    assert torch.cuda.current_device() == cur
+    sid, rid = r.add_source(make_source(1, 16000)), r.add_rirs([make_rir(1, 3000)])[0]
+    spec = r.render([AudioRequest(rir=rid, source=sid)])
+    torch.cuda.synchronize(r.device)
+    assert torch.cuda.current_device() == cur and spec.device == r.device
+    ref = ao.compute_spectrogram(ao.compute_audiogoal(make_source(1, 16000), make_rir(1, 3000), 16000).astype(np.float32))
+    assert np.allclose(spec[0].cpu().numpy(), ref, rtol=1e-4, atol=1e-5)

@@ -44,11 +44,14 @@ _renderers = {}
 
 
 def renderer(sr, max_taps, n_terms=1, log2n=0, pad_mode="reflect"):
+    """log2n 12 / 13 / 14: the partitioned plan at that block size.  log2n 0 HERE: the renderer prefers the
+    single-block plan (65536-point cluster kernel) for every batch that fits it and falls back to the partitioned
+    default otherwise (prefer_block64=True; the library default prefers the partitioned plan, the faster one)."""
     from soundspaces_b200 import BatchedAudioRenderer
     key = (sr, max_taps, n_terms, log2n, pad_mode)
     if key not in _renderers:
         _renderers[key] = BatchedAudioRenderer(sr, max_taps, device="cuda:0", n_terms=n_terms, log2n=log2n,
-                                               pad_mode=pad_mode)
+                                               pad_mode=pad_mode, prefer_block64=(log2n == 0))
     return _renderers[key]
 
 
@@ -58,12 +61,14 @@ def golden_wave(golden, name):
     return golden[f"{name}/wave_stride5"], 5
 
 
-@pytest.mark.parametrize("log2n", [13, 12, 14])
+@pytest.mark.parametrize("log2n", [13, 12, 14, 0])
 @pytest.mark.parametrize("name", sorted(mg.DISCRETE_CASES))
 def test_discrete_golden(golden, name, log2n):
+    """log2n 12/13/14: the partitioned plan at that block size; 0: the default, i.e. the single-block 65536-point
+    cluster kernel whenever the request fits it (one term, <= 65536 - sr + 1 effective taps), else partitioned."""
     from soundspaces_b200 import AudioRequest
     c = mg.DISCRETE_CASES[name]
-    if log2n != 13 and name not in ("a2_16k", "a4_valid", "a5_distractor", "a2_44k"):
+    if log2n not in (0, 13) and name not in ("a2_16k", "a4_valid", "a5_distractor", "a2_44k"):
         pytest.skip("other FFT sizes are exercised on a subset")
     src, rir, dsrc, drir = mg.discrete_inputs(c)
     sr = c["sr"]
@@ -77,7 +82,13 @@ def test_discrete_golden(golden, name, log2n):
         if dsrc is not None:
             req.distractor_source = r.add_source(dsrc)
             req.distractor_rir = r.add_rirs([drir])[0]
-        spec, wave = r.render([req], want_wave=True)
+        batch = r.prepare([req])
+        fits = dsrc is None and min(len(rir), req.offset + sr) <= 65536 - sr + 1
+        if log2n == 0 and fits and not req.silent:
+            assert batch.plan.log2n == 16, "eligible request must take the single-block plan"
+        if log2n != 0 or not fits:
+            assert batch.plan.log2n != 16
+        spec, wave = r.execute(batch, want_wave=True)
         torch.cuda.synchronize()
         gw, stride = golden_wave(golden, name)
         check_wave(wave[0].cpu().numpy(), gw, stride)
@@ -146,13 +157,14 @@ def test_singing_fixture(golden):
     check_spec(spec[0].cpu().numpy(), golden["singing/spec_reflect"])
 
 
-@pytest.mark.parametrize("conv_mode", [0, 1])
-def test_ragged_batch_matches_oracle(conv_mode):
-    """Mixed batch: ragged RIR lengths, zero-RIR fallback, silent envs, different offsets; both
-    convolution schedules (per-bin partition sums / fused into the inverse FFT)."""
+@pytest.mark.parametrize("log2n,conv_mode", [(13, 0), (13, 1), (0, 0)])
+def test_ragged_batch_matches_oracle(log2n, conv_mode):
+    """Mixed batch: ragged RIR lengths, zero-RIR fallback, silent envs, different offsets; the partitioned plan with
+    both schedules (per-bin partition sums / fused into the inverse FFT) and the single-block plan (log2n 0:
+    every request here fits it: 48000 taps <= 65536 - 16000 + 1)."""
     from soundspaces_b200 import AudioRequest
     sr = 16000
-    r = renderer(sr, 48000, n_terms=2)
+    r = renderer(sr, 48000, n_terms=2, log2n=log2n)
     r.set_conv_mode(conv_mode)
     clips = [make_source(40, sr), make_source(41, 5 * sr)]
     sids = [r.add_source(c) for c in clips]
@@ -165,7 +177,9 @@ def test_ragged_batch_matches_oracle(conv_mode):
             silent = (i + off // sr) % 7 == 3
             reqs.append(AudioRequest(rir=rid, source=sids[s], offset=off, silent=silent))
             refs.append(ao.compute_audiogoal(clips[s], rirs[i], sr, silent=silent, audio_index=off // sr))
-    spec, wave = r.render(reqs, want_wave=True)
+    batch = r.prepare(reqs)
+    assert batch.plan.log2n == (16 if log2n == 0 else log2n)
+    spec, wave = r.execute(batch, want_wave=True)
     torch.cuda.synchronize()
     spec, wave = spec.cpu().numpy(), wave.cpu().numpy()
     for i, ref in enumerate(refs):
@@ -190,10 +204,19 @@ def test_full_size_c2_properties():
     rirs[64] = 2.0 * rirs[0] - 0.5 * rirs[1]                        # linear combination
     ids = r.add_rirs(list(rirs))
     reqs = [AudioRequest(rir=i, source=sid, silent=(k == 9)) for k, i in enumerate(ids)]
+    assert r.prepare(reqs).plan.log2n == 16          # config 2 runs on the single-block cluster kernel
     spec, wave = r.render(reqs, want_wave=True)
     torch.cuda.synchronize()
     spec_h, wave_h = spec.cpu().numpy(), wave.cpu().numpy()
     assert spec_h.shape == (B, 65, 69, 2) and wave_h.shape == (B, 2, sr)
+    # the partitioned plan on the same batch agrees to rounding (two different FFT factorizations)
+    rp = renderer(sr, L, log2n=12)
+    idp = rp.add_rirs(list(rirs))
+    sidp = rp.add_source(src)
+    wave_p = rp.render([AudioRequest(rir=i, source=sidp, silent=(k == 9)) for k, i in enumerate(idp)], want_wave=True)[1]
+    torch.cuda.synchronize()
+    dp = np.abs(wave_p.cpu().numpy() - wave_h).max(axis=(1, 2))
+    assert (dp <= 3e-6 * np.abs(wave_h).max()).all()
     for i in (0, 1, 31, 127):
         w_ref, s_ref = ao.render_frame(src, rirs[i], sr)
         check_wave(wave_h[i], w_ref)
@@ -306,13 +329,14 @@ def test_savi_pretraining_dataset_quirk():
         check_spec(spec[k].cpu().numpy(), ao.compute_spectrogram(ref.astype(np.float32)))
 
 
-def test_full_size_c3_head_and_valid():
-    """BASELINE config 3 at full size on one GPU's share and beyond: 16 kHz, 48000-tap RIRs (3 s reverb), 512 envs;
+@pytest.mark.parametrize("log2n", [0, 13])
+def test_full_size_c3_head_and_valid(log2n):
+    """(log2n 0: single-block cluster kernel, 13: partitioned plan.)  BASELINE config 3 at full size on one GPU's share and beyond: 16 kHz, 48000-tap RIRs (3 s reverb), 512 envs;
     "head" mode (1-s clip: only the first 16000 taps matter) and "valid" mode (4-s clip, steady state: all 48000
     taps).  Spot checks against the oracle + exact zeros for silent / zero-RIR envs."""
     from soundspaces_b200 import AudioRequest
     sr, L, B = 16000, 48000, 512
-    r = renderer(sr, L)
+    r = renderer(sr, L, log2n=log2n)
     clip1, clip4 = make_source(80, sr), make_source(81, 4 * sr)
     s1, s4 = r.add_source(clip1), r.add_source(clip4)
     rng = np.random.default_rng(5)
@@ -324,6 +348,7 @@ def test_full_size_c3_head_and_valid():
     rirs_h = rirs.numpy()
     for mode, sid, clip, off in (("head", s1, clip1, 0), ("valid", s4, clip4, 3 * sr)):
         reqs = [AudioRequest(rir=i, source=sid, offset=off, silent=(k == 11)) for k, i in enumerate(ids)]
+        assert r.prepare(reqs).plan.log2n == (16 if log2n == 0 else log2n)
         spec, wave = r.render(reqs, want_wave=True)
         torch.cuda.synchronize()
         assert spec.shape == (B, 65, 26, 2)
@@ -419,11 +444,13 @@ def test_randomised_requests(log2n, conv_mode):
     r.set_conv_mode(0)
 
 
-def test_window_pool_recycling():
-    """A tiny window-spectra pool is recycled mid-batch; prepare() restarts and results stay correct."""
+@pytest.mark.parametrize("log2n", [12, 0])
+def test_window_pool_recycling(log2n):
+    """A tiny source-spectra pool is recycled mid-batch; prepare() restarts and results stay correct (partitioned
+    plan: 64 windows; single-block plan: 8 spectra of 65536 points)."""
     from soundspaces_b200 import AudioRequest, BatchedAudioRenderer
     sr = 16000
-    r = BatchedAudioRenderer(sr, 8192, device="cuda:0", xpool_bytes=1)      # minimum pool: 64 windows
+    r = BatchedAudioRenderer(sr, 8192, device="cuda:0", xpool_bytes=1, log2n=log2n, prefer_block64=(log2n == 0))      # minimum pool
     clip = make_source(33, 6 * sr)
     sid = r.add_source(clip)
     rir = make_rir(34, 5000)

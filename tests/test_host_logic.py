@@ -164,13 +164,15 @@ def _host_only_renderer(n_terms=2):
     plan.log2n, plan.block, plan.sr, plan.n_blocks, plan.max_parts, plan.n_terms = 12, 2048, 16000, 8, 10, n_terms
     plan.h_elems_per_env = n_terms * 10 * 4096
     r.plan = plan
+    r.plan64, r.block64_taps, r.force_block64 = None, 65536 - 16000 + 1, False     # partitioned plan only
     r.device = torch.device("cpu")
     r._bank_index = None
     r._rir_len = [100, 4097, 0, 20000, 9000, 16000]
     r._rir_off = [0, 100, 0, 4197, 24197, 33197]
     calls = []
 
-    def windows(source, offset, wrap, out_samples):            # deterministic stand-in for the cached spectra
+    def windows(source, offset, wrap, out_samples, block64=False):   # deterministic stand-in for the cached spectra
+        assert not block64
         calls.append((source, offset, wrap, out_samples))
         nblk, wofs, nw = window_layout(r.P, plan.max_parts, offset, out_samples)
         return (1000 * source + offset + 7 * int(wrap) + out_samples, nw, wofs)
