@@ -25,6 +25,8 @@
  *                              of the reference hands over), copies included
  *   ssb_sh_decode_batch     <- scripts/ambisonic_to_binaural.py:14-19 (closed AmbisonicBinauralizer ELF)
  *   ssb_intensity_batch     <- Intensity.get_observation, ss_baselines/av_wan/avwan_sensors.py:91-100
+ *   ssb_audio_conv1_batch   <- permute(0, 3, 1, 2) + the first Conv2d + ReLU of AudioCNN,
+ *                              ss_baselines/av_nav/models/audio_cnn.py:51-58,86 (rollout-time forward)
  *   ssb_logmel_batch        <- EXTENSION (no reference code): the log-mel front end BASELINE.json configs[2] names;
  *                              log1p(librosa.feature.melspectrogram) on the reference's STFT geometry (nav.py:89-92)
  *   ssb_pcm16_decode/encode <- int16 <-> float32 PCM (librosa.load decode used at
@@ -210,6 +212,15 @@ int ssb_logmel_frames(int sr);
 int ssb_mel_filterbank(int sr, int n_mels, float* h_out);
 int ssb_logmel_batch(ssb_ctx* ctx, int B, const float* d_wave, int64_t wave_stride, int sr, int n_mels, int power,
                      int pad_mode, float* d_out, void* stream);
+
+/* first layer of the policy's audio encoder, fused with the layout change.  AudioCNN.forward
+ * (ss_baselines/av_nav/models/audio_cnn.py:79-89) permutes the observation to channels-first and applies
+ * Conv2d(2 -> OC, KHxKW, stride SHxSW, no padding) [+ ReLU]; this reads d_spec[env][H][W][2] (the layout
+ * ssb_spectrogram_batch writes) and writes d_out[env][OC][H1][W1], H1 = (H-KH)/SH + 1, W1 = (W-KW)/SW + 1.
+ * d_weight: [OC][2][KH][KW] (torch's Conv2d.weight), d_bias: [OC] or NULL.  Inference only.  SSB_E_SHAPE when
+ * W1 * OC > 1024 or the staged rows + weights exceed 48 KB. */
+int ssb_audio_conv1_batch(ssb_ctx* ctx, int B, const float* d_spec, int H, int W, const float* d_weight,
+                          const float* d_bias, int OC, int KH, int KW, int SH, int SW, int relu, float* d_out, void* stream);
 
 /* PCM helpers.  decode: float32(x) / 32768 (exact).  encode mode 0: round(x*32768) saturated;
  * mode 1: trunc(x*32767) saturated (interactive_demo.py:110). */

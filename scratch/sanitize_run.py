@@ -34,6 +34,25 @@ for pm in ("reflect", "constant"):                                       # log-m
     for n_mels, power in ((64, 2), (13, 1), (1, 2)):
         rm.logmel(wave[:5].clone(), n_mels=n_mels, power=power)
 torch.cuda.synchronize()
+# single-block plan: the 65536-point cluster kernel (named group barriers, in-place staging, DSMEM combine) + its
+# source-spectrum kernel: short / long (> 16384 taps: q2 loop) / zero RIRs, offsets, wrap, truncated outputs, silent
+for sr in (16000, 44100):
+    rb = BatchedAudioRenderer(sr, min(48000, 65536 - sr + 1), prefer_block64=True)
+    s1 = rb.add_source(make_source(1, sr)); s2 = rb.add_source(make_source(2, 3 * sr))
+    ids = rb.add_rirs([make_rir(i, L) for i, L in enumerate((100, 4097, 16384, min(48000, 65536 - sr + 1)))] + [None])
+    reqs = [AudioRequest(rir=ids[0], source=s1), AudioRequest(rir=ids[1], source=s2, offset=sr),
+            AudioRequest(rir=ids[3], source=s2, offset=2 * sr), AudioRequest(rir=ids[2], source=s2, offset=8000, out_samples=4000, wrap=True),
+            AudioRequest(rir=ids[4], source=s1), AudioRequest(rir=ids[0], source=s1, silent=True)]
+    batch = rb.prepare(reqs)
+    assert batch.plan.log2n == 16
+    rb.execute(batch, want_wave=True)
+    torch.cuda.synchronize()
+# fused first layer of the audio encoder
+from soundspaces_b200.renderer import WaveformOps
+for shape, k, st in (((3, 65, 69, 2), 8, 4), ((3, 65, 26, 2), 5, 2)):
+    conv = torch.nn.Conv2d(2, 32, k, st).cuda()
+    WaveformOps.get("cuda:0").audio_conv1(torch.rand(shape, device="cuda"), conv)
+torch.cuda.synchronize()
 hs = r.make_host_session(8, 3000, want_wave=True, n_chunks=2)
 hs.h_rir.numpy()[:] = np.stack([make_rir(i, 3000) for i in range(8)]); hs.set_requests(sid); hs.run(); hs.run()
 torch.cuda.synchronize()

@@ -939,6 +939,41 @@ intensity_kernel(const float* __restrict__ wave, long long wave_stride, int sr, 
     if (t == 0) out[env] = end > idx ? sf[0] / (float)(2 * (end - idx)) : nanf("");
 }
 
+// ---------------------------------------------------------------------------
+// the first layer of the policy's audio encoder fused with the layout change.  AudioCNN.forward
+// (ss_baselines/av_nav/models/audio_cnn.py:79-89) permutes the (N, 65, T', 2) observation to (N, 2, 65, T') and runs
+// Conv2d(2 -> 32, 8x8 / 4, or 5x5 / 2 for inputs under 30 pixels) + ReLU; here the convolution reads the observation
+// in the layout the spectrogram kernel wrote it (ears interleaved) and writes (N, OC, H1, W1): no permuted copy, one
+// launch.  Inference only (rollout collection runs under no_grad, ppo_trainer.py:131-146); the PPO update keeps
+// PyTorch's layer.  grid (H1, N); block (W1 * OC) <= 1024; dynamic smem: KH input rows + all weights.
+// ---------------------------------------------------------------------------
+__global__ void audio_conv1_kernel(const float* __restrict__ spec, int H, int W, const float* __restrict__ weight,
+                                   const float* __restrict__ bias, int OC, int KH, int KW, int SH, int SW, int H1, int W1,
+                                   int relu, float* __restrict__ out) {
+    extern __shared__ float c1_smem[];
+    float* rows = c1_smem;                                  // [KH][W][2]
+    float* wsm = c1_smem + KH * W * 2;                      // [OC][2][KH][KW]
+    const int oh = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+    const float* __restrict__ in = spec + ((long long)n * H + (long long)oh * SH) * W * 2;
+    for (int i = tid; i < KH * W * 2; i += blockDim.x) rows[i] = __ldg(in + i);
+    for (int i = tid; i < OC * 2 * KH * KW; i += blockDim.x) wsm[i] = __ldg(weight + i);
+    __syncthreads();
+    const int ow = tid % W1, oc = tid / W1;
+    if (oc >= OC) return;
+    float acc = bias ? __ldg(bias + oc) : 0.f;
+    const float* __restrict__ w0 = wsm + (oc * 2 + 0) * KH * KW;
+    const float* __restrict__ w1 = wsm + (oc * 2 + 1) * KH * KW;
+    for (int kh = 0; kh < KH; ++kh) {
+        const float* __restrict__ r = rows + (kh * W + ow * SW) * 2;
+        for (int kw = 0; kw < KW; ++kw) {
+            acc = fmaf(r[2 * kw], w0[kh * KW + kw], acc);           // channel 0 = left ear
+            acc = fmaf(r[2 * kw + 1], w1[kh * KW + kw], acc);       // channel 1 = right ear
+        }
+    }
+    if (relu) acc = fmaxf(acc, 0.f);
+    out[(((long long)n * OC + oc) * H1 + oh) * W1 + ow] = acc;
+}
+
 __global__ void pcm16_decode_kernel(const int16_t* __restrict__ in, long long n, float* __restrict__ out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x;
@@ -1704,6 +1739,25 @@ extern "C" int ssb_host_copy_bytes(const ssb_ctx* ctx, int64_t* h2d, int64_t* d2
     return SSB_OK;
 }
 
+static int ssb_audio_conv1_batch_impl(ssb_ctx* ctx, int B, const float* d_spec, int H, int W, const float* d_weight,
+                                      const float* d_bias, int OC, int KH, int KW, int SH, int SW, int relu, float* d_out,
+                                      void* stream) {
+    if (B == 0) return SSB_OK;
+    if (B < 0 || B > 65535 || !d_spec || !d_weight || !d_out || H < 1 || W < 1 || OC < 1 || KH < 1 || KW < 1 || SH < 1 || SW < 1 ||
+        KH > H || KW > W)
+        SSB_FAIL(ctx, SSB_E_INVALID_ARG, "ssb_audio_conv1_batch: bad arguments (B=%d H=%d W=%d OC=%d K=%dx%d S=%dx%d)", B, H, W, OC, KH,
+                 KW, SH, SW);
+    const int H1 = (H - KH) / SH + 1, W1 = (W - KW) / SW + 1;
+    const size_t smem = ((size_t)KH * W * 2 + (size_t)OC * 2 * KH * KW) * sizeof(float);
+    if (W1 * OC > 1024 || smem > 48 * 1024)
+        SSB_FAIL(ctx, SSB_E_SHAPE, "ssb_audio_conv1_batch: layer too large for the fused kernel (W1*OC=%d, smem=%zu)", W1 * OC, smem);
+    audio_conv1_kernel<<<dim3(H1, B), W1 * OC, smem, (cudaStream_t)stream>>>(d_spec, H, W, d_weight, d_bias, OC, KH, KW, SH, SW, H1, W1,
+                                                                          relu, d_out);
+    ctx->launches += 1;
+    SSB_CUDA(ctx, cudaGetLastError());
+    return SSB_OK;
+}
+
 static int ssb_pcm16_decode_impl(ssb_ctx* ctx, const int16_t* d_in, int64_t n, float* d_out, void* stream) {
     if (!ctx) return SSB_E_INVALID_ARG;
     if (n == 0) return SSB_OK;
@@ -1790,4 +1844,9 @@ extern "C" int ssb_pcm16_decode(ssb_ctx* ctx, const int16_t* d_in, int64_t n, fl
 
 extern "C" int ssb_pcm16_encode(ssb_ctx* ctx, const float* d_in, int64_t n, int mode, int16_t* d_out, void* stream) {
     return abi_call(ctx, [&] { return ssb_pcm16_encode_impl(ctx, d_in, n, mode, d_out, stream); });
+}
+extern "C" int ssb_audio_conv1_batch(ssb_ctx* ctx, int B, const float* d_spec, int H, int W, const float* d_weight,
+                                     const float* d_bias, int OC, int KH, int KW, int SH, int SW, int relu, float* d_out,
+                                     void* stream) {
+    return abi_call(ctx, [&] { return ssb_audio_conv1_batch_impl(ctx, B, d_spec, H, W, d_weight, d_bias, OC, KH, KW, SH, SW, relu, d_out, stream); });
 }

@@ -120,6 +120,26 @@ class WaveformOps:
                        "ssb_intensity_batch")
         return out
 
+    @torch.no_grad()
+    def audio_conv1(self, spec: torch.Tensor, conv: "torch.nn.Conv2d", relu: bool = True) -> torch.Tensor:
+        """``relu(conv(spec.permute(0, 3, 1, 2)))`` for the first layer of ``AudioCNN``
+        (audio_cnn.py:51-58,86) straight from the (n, 65, T', 2) observation: no permuted copy, one launch.
+        Inference only (rollout collection); ``conv`` must be an unpadded, undilated 2-input-channel ``Conv2d``."""
+        if not (spec.is_cuda and spec.dtype == torch.float32 and spec.ndim == 4 and spec.shape[3] == 2 and spec.is_contiguous()):
+            raise ValueError("expected a contiguous CUDA float32 (n, H, W, 2) observation")
+        if (conv.in_channels != 2 or tuple(conv.padding) != (0, 0) or tuple(conv.dilation) != (1, 1) or conv.groups != 1
+                or conv.padding_mode != "zeros"):
+            raise ValueError("audio_conv1 fuses Conv2d(2 -> OC, k, stride) without padding / dilation / groups")
+        n, H, W, _ = spec.shape
+        (kh, kw), (sh, sw) = conv.kernel_size, conv.stride
+        out = torch.empty((n, conv.out_channels, (H - kh) // sh + 1, (W - kw) // sw + 1), dtype=torch.float32, device=self.device)
+        w = conv.weight.detach().to(self.device, torch.float32).contiguous()
+        b = conv.bias.detach().to(self.device, torch.float32).contiguous() if conv.bias is not None else None
+        self.ctx.check(self.lib.ssb_audio_conv1_batch(
+            self.ctx.handle, n, spec.data_ptr(), H, W, w.data_ptr(), b.data_ptr() if b is not None else None,
+            conv.out_channels, kh, kw, sh, sw, int(bool(relu)), out.data_ptr(), self._stream()), "ssb_audio_conv1_batch")
+        return out
+
 
 class BatchedAudioRenderer:
     def __init__(self, sr: int, max_taps: int, device="cuda:0", n_terms: int = 1, log2n: int = 0,

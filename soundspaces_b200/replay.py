@@ -66,7 +66,7 @@ class ReplayScene:
         ids = service.renderer.add_rirs(flat)
         for k, i in zip(keys, ids):
             service._rir_ids[k] = i
-            service._touched[k] = service._step
+            service._touched.setdefault(k, 0)
         return ids
 
 
@@ -198,8 +198,18 @@ class AudioPolicy(nn.Module):
         return self.actor(f), self.critic(f)
 
     @torch.no_grad()
-    def act(self, spectrogram: torch.Tensor):
-        logits, value = self.forward(spectrogram)
+    def forward_fused(self, spectrogram: torch.Tensor):
+        """Rollout-time forward with the first layer fused: permute + Conv2d + ReLU of ``cnn[0:2]``
+        run as ONE kernel straight from the (N, 65, T', 2) observation (``WaveformOps.audio_conv1``)."""
+        from .renderer import WaveformOps
+        if self.channels_first or not spectrogram.is_cuda:
+            return self.forward(spectrogram)
+        f = self.cnn[2:](WaveformOps.get(spectrogram.device).audio_conv1(spectrogram.contiguous(), self.cnn[0], relu=True))
+        return self.actor(f), self.critic(f)
+
+    @torch.no_grad()
+    def act(self, spectrogram: torch.Tensor, fused: bool = False):
+        logits, value = self.forward_fused(spectrogram) if fused else self.forward(spectrogram)
         dist = torch.distributions.Categorical(logits=logits)
         actions = dist.sample()
         return value, actions, dist.log_prob(actions)

@@ -32,7 +32,6 @@ from __future__ import annotations
 import logging
 import os
 import threading
-from collections import OrderedDict
 from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Dict, Optional
 
@@ -92,9 +91,10 @@ class AudioRenderService:
             sr, self.max_taps, device=device, n_terms=n_terms, log2n=log2n, pad_mode=pad_mode)
         self._kwargs = dict(max_taps=self.max_taps, n_terms=n_terms, log2n=log2n, max_bank_bytes=self.max_bank_bytes)
         self._rir_ids: Dict[object, int] = {}        # key (path or (dir, az, r, s)) -> bank id
-        self._touched: "OrderedDict[object, int]" = OrderedDict()   # key -> step of last use (LRU order)
+        self._touched: Dict[object, int] = {}        # key -> step of last use (sorted only when the bank is compacted)
         self._src_ids: Dict[tuple, tuple] = {}
         self._step = 0
+        self._clock = 0                               # use counter behind the LRU order
         self._pool = ThreadPoolExecutor(max_workers=prefetch_workers, thread_name_prefix="ssb-rir") if prefetch_workers else None
         self._inflight: Dict[object, object] = {}    # key -> Future of _read_rir_file
         self._lock = threading.Lock()
@@ -140,7 +140,7 @@ class AudioRenderService:
             return                                    # queued requests already hold bank ids: compact after their flush
         if r.bank_bytes > self.max_bank_bytes:
             keep, kept_bytes = [], 0
-            for key in reversed(self._touched):                     # most recent first
+            for key in sorted(self._touched, key=self._touched.get, reverse=True):      # most recently used first
                 rid = self._rir_ids.get(key)
                 if rid is None:
                     continue
@@ -152,7 +152,7 @@ class AudioRenderService:
             keep.reverse()
             new_ids = r.compact_bank([self._rir_ids[k] for k in keep])
             self._rir_ids = {k: i for k, i in zip(keep, new_ids)}
-            self._touched = OrderedDict((k, self._touched[k]) for k in keep)
+            self._touched = {k: self._touched[k] for k in keep}
             self.stats["compactions"] += 1
 
     def prefetch(self, keys):
@@ -180,16 +180,19 @@ class AudioRenderService:
         ids = self.renderer.add_rirs(rirs)
         for k, i in zip(done, ids):
             self._rir_ids[k] = i
-            self._touched[k] = self._step
+            self._touched.setdefault(k, 0)            # prefetched, not used yet: first to go
         self.stats["prefetched"] += len(done)
 
     def rir(self, key) -> int:
         """Bank id of an RIR file; ``key`` is the path, or ``(binaural_rir_dir, azimuth, receiver, source)``
         (formatted into the reference's path only when the file has to be opened)."""
         rid = self._rir_ids.get(key)
-        if rid is not None:
+        if rid is not None:                           # the per-env hot path: two dict operations
             self.stats["hits"] += 1
-        elif key in self._inflight:
+            self._clock += 1
+            self._touched[key] = self._clock
+            return rid
+        if key in self._inflight:
             self.stats["waited"] += 1
             self.poll(wait_for=key)
             rid = self._rir_ids.get(key)
@@ -199,8 +202,8 @@ class AudioRenderService:
             self.stats["misses"] += 1
             rid = self.renderer.add_rirs([_read_rir_file(self._path_of(key))])[0]
             self._rir_ids[key] = rid
-        self._touched[key] = self._step
-        self._touched.move_to_end(key)
+        self._clock += 1
+        self._touched[key] = self._clock
         return rid
 
     rir_from_file = rir

@@ -83,7 +83,7 @@ def test_discrete_golden(golden, name, log2n):
             req.distractor_source = r.add_source(dsrc)
             req.distractor_rir = r.add_rirs([drir])[0]
         batch = r.prepare([req])
-        fits = dsrc is None and min(len(rir), req.offset + sr) <= 65536 - sr + 1
+        fits = dsrc is None and min(len(rir) if rir is not None else 0, req.offset + sr) <= 65536 - sr + 1
         if log2n == 0 and fits and not req.silent:
             assert batch.plan.log2n == 16, "eligible request must take the single-block plan"
         if log2n != 0 or not fits:

@@ -101,3 +101,29 @@ def test_rollout_slots_equal_the_oracle():
                 s.step(int(trace[step, e]))
     logits, value = policy(storage[3])
     assert logits.shape == (n_envs, 4) and value.shape == (n_envs, 1) and torch.isfinite(logits).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(65, 69, 2), (65, 26, 2)])
+def test_fused_first_conv_matches_torch(shape):
+    """permute + first Conv2d + ReLU of AudioCNN as one kernel from the (N, 65, T', 2) observation, against
+    PyTorch's float64 convolution of the permuted tensor (audio_cnn.py:51-58,86); then the whole fused forward."""
+    from soundspaces_b200.renderer import WaveformOps
+    torch.manual_seed(0)
+    policy = AudioPolicy(shape).cuda()
+    conv = policy.cnn[0]
+    assert conv.kernel_size == ((8, 8) if shape[1] >= 30 else (5, 5))
+    spec = torch.rand((9,) + shape, device="cuda") * 3.0
+    got = WaveformOps.get("cuda:0").audio_conv1(spec, conv, relu=True)
+    ref = torch.relu(torch.nn.functional.conv2d(spec.permute(0, 3, 1, 2).double().cpu(), conv.weight.double().cpu(),
+                                                conv.bias.double().cpu(), stride=conv.stride))
+    assert got.shape == ref.shape
+    assert torch.allclose(got.cpu().double(), ref, rtol=1e-5, atol=1e-5)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        la, va = policy.forward(spec)
+        lb, vb = policy.forward_fused(spec)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert torch.allclose(la, lb, rtol=1e-4, atol=1e-4) and torch.allclose(va, vb, rtol=1e-4, atol=1e-4)
