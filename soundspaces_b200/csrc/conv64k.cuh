@@ -95,18 +95,25 @@ src64k_kernel(const float* __restrict__ src, int S, long long m0, int wrap, int 
     for (int i = 0; i < 16; ++i) SX[(long long)r * C64_NS + i * P::T + t] = v[i];
 }
 
-// grid (4 * B), cluster (4,1,1), block 1024, dynamic smem C64_SMEM_BYTES.
-__global__ void __cluster_dims__(C64_CL, 1, 1) __launch_bounds__(C64_TPB, 1)
+// grid (4 * B), cluster (4,1,1), block 256 * NG, dynamic smem C64_SMEM_BYTES.
+// NG = groups of 256 threads per CTA.  NG = 4: the CTA's four sub-problems are transformed side by side (1024 threads,
+// the whole register file of the SM).  NG = 2: two rounds of two (512 threads, 64 registers: half the register file and
+// 48 warp slots stay free, so CTAs of the spectrogram kernel launched on another stream can be co-resident and fill
+// this kernel's memory / barrier phases).  In the staging phases (A, E, F) a thread plays 4 / NG "virtual" threads.
+template <int NG>
+__global__ void __cluster_dims__(C64_CL, 1, 1) __launch_bounds__(256 * NG, NG == 4 ? 1 : 2)
 conv64k_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ rir_bank, const float2* __restrict__ xpool,
                float* __restrict__ wave, long long wave_stride, int sr, const float2* __restrict__ tw12,
                const float2* __restrict__ twm) {
     using P = FftPlan<12>;
+    constexpr int NT = 256 * NG;                        // physical threads
+    constexpr int NV = C64_TPB / NT;                    // virtual threads per physical thread in the staging phases
     extern __shared__ float2 smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int c = (int)cluster.block_rank();            // residue class of the spectrum bins this CTA owns
     const int env = blockIdx.x / C64_CL;
-    const int tau = threadIdx.x;
-    const int m = tau >> 8, t = tau & 255;              // group / thread within the group
+    const int t = threadIdx.x & 255;                    // thread within its group
+    const int grp = threadIdx.x >> 8;
     const ssb_req& rq = reqs[env];
     const int taps = (rq.flags & SSB_FLAG_SILENT) ? 0 : rq.term[0].rir_taps;
     const int nvalid = taps > 0 ? min(rq.out_samples, sr) : 0;
@@ -114,11 +121,13 @@ conv64k_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ rir_
     float* __restrict__ wl = wave + (long long)env * 2 * wave_stride;
     float* __restrict__ wr = wl + wave_stride;
     if (nvalid == 0) {                                  // silent / zero RIR: exact zeros (cluster-uniform exit)
-        for (int n = c * C64_TPB + tau; n < sr; n += C64_CL * C64_TPB) { wl[n] = 0.f; wr[n] = 0.f; }
+        for (int n = c * NT + threadIdx.x; n < sr; n += C64_CL * NT) { wl[n] = 0.f; wr[n] = 0.f; }
         return;
     }
     // ---- phase A: modulate by the residue class, radix-4 over q1 (and q2 for taps > 16384), twiddle -> a_r[n1]
-    {
+#pragma unroll 1
+    for (int vt = 0; vt < NV; ++vt) {
+        const int tau = threadIdx.x + vt * NT;          // virtual thread 0..1023
         float2 twr[4];                                  // w_M^(tau r), r = c + 4 m' (re-read in phase E: 8 registers less across the transforms)
 #pragma unroll
         for (int mm = 0; mm < 4; ++mm) twr[mm] = __ldg(twm + (c + 4 * mm) * 1024 + tau);
@@ -169,10 +178,12 @@ conv64k_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ rir_
     }
     __syncthreads();
 
-    // ---- phases B-D: group m transforms sub-problem r = c + 4 m, multiplies by the source spectrum, transforms back
-    {
+    // ---- phases B-D: group grp transforms sub-problem r = c + 4 m, multiplies by the source spectrum, transforms back
+#pragma unroll 1
+    for (int round = 0; round < NV; ++round) {
+        const int m = round * NG + grp;
         float2* __restrict__ buf = smem + m * C64_BUF;
-        const GroupBar bar{1 + m};
+        const GroupBar bar{1 + grp};
         const int r = c + 4 * m;
         float2 v[16];
 #pragma unroll
@@ -198,63 +209,70 @@ conv64k_kernel(const ssb_req* __restrict__ reqs, const float2* __restrict__ rir_
     __syncthreads();
 
     // ---- phase E: conj twiddle, inverse radix-4 over m', demodulate; in place: buffer q1 <- v_c[q1][n1]
-    float2 twr[4];
+#pragma unroll 1
+    for (int vt = 0; vt < NV; ++vt) {
+        const int tau = threadIdx.x + vt * NT;
+        float2 twr[4];
 #pragma unroll
-    for (int mm = 0; mm < 4; ++mm) twr[mm] = __ldg(twm + (c + 4 * mm) * 1024 + tau);
+        for (int mm = 0; mm < 4; ++mm) twr[mm] = __ldg(twm + (c + 4 * mm) * 1024 + tau);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n1 = tau + 1024 * i;
-        float2 b[4];
-        b[0] = cmulc(smem[0 * C64_BUF + n1], twr[0]);
-        if (i == 0) {
-            b[1] = cmulc(smem[1 * C64_BUF + n1], twr[1]);
-            b[2] = cmulc(smem[2 * C64_BUF + n1], twr[2]);
-            b[3] = cmulc(smem[3 * C64_BUF + n1], twr[3]);
-        } else if (i == 1) {
-            b[1] = mul_w16<true, 1>(cmulc(smem[1 * C64_BUF + n1], twr[1]));
-            b[2] = mul_w16<true, 2>(cmulc(smem[2 * C64_BUF + n1], twr[2]));
-            b[3] = mul_w16<true, 3>(cmulc(smem[3 * C64_BUF + n1], twr[3]));
-        } else if (i == 2) {
-            b[1] = mul_w16<true, 2>(cmulc(smem[1 * C64_BUF + n1], twr[1]));
-            b[2] = mul_w16<true, 4>(cmulc(smem[2 * C64_BUF + n1], twr[2]));
-            b[3] = mul_w16<true, 6>(cmulc(smem[3 * C64_BUF + n1], twr[3]));
-        } else {
-            b[1] = mul_w16<true, 3>(cmulc(smem[1 * C64_BUF + n1], twr[1]));
-            b[2] = mul_w16<true, 6>(cmulc(smem[2 * C64_BUF + n1], twr[2]));
-            b[3] = mul_w16<true, 9>(cmulc(smem[3 * C64_BUF + n1], twr[3]));
+        for (int i = 0; i < 4; ++i) {
+            const int n1 = tau + 1024 * i;
+            float2 b[4];
+            b[0] = cmulc(smem[0 * C64_BUF + n1], twr[0]);
+            if (i == 0) {
+                b[1] = cmulc(smem[1 * C64_BUF + n1], twr[1]);
+                b[2] = cmulc(smem[2 * C64_BUF + n1], twr[2]);
+                b[3] = cmulc(smem[3 * C64_BUF + n1], twr[3]);
+            } else if (i == 1) {
+                b[1] = mul_w16<true, 1>(cmulc(smem[1 * C64_BUF + n1], twr[1]));
+                b[2] = mul_w16<true, 2>(cmulc(smem[2 * C64_BUF + n1], twr[2]));
+                b[3] = mul_w16<true, 3>(cmulc(smem[3 * C64_BUF + n1], twr[3]));
+            } else if (i == 2) {
+                b[1] = mul_w16<true, 2>(cmulc(smem[1 * C64_BUF + n1], twr[1]));
+                b[2] = mul_w16<true, 4>(cmulc(smem[2 * C64_BUF + n1], twr[2]));
+                b[3] = mul_w16<true, 6>(cmulc(smem[3 * C64_BUF + n1], twr[3]));
+            } else {
+                b[1] = mul_w16<true, 3>(cmulc(smem[1 * C64_BUF + n1], twr[1]));
+                b[2] = mul_w16<true, 6>(cmulc(smem[2 * C64_BUF + n1], twr[2]));
+                b[3] = mul_w16<true, 9>(cmulc(smem[3 * C64_BUF + n1], twr[3]));
+            }
+            bfly4<true>(b[0], b[1], b[2], b[3]);                            // b[q1] = sum_m' conj(w4)^(q1 m') b[m']
+            if (c != 0) {
+#pragma unroll
+                for (int q1 = 0; q1 < 4; ++q1) b[q1] = cmulc(b[q1], kW64[((4 * q1 + i) * c) & 63]);
+            }
+#pragma unroll
+            for (int q1 = 0; q1 < 4; ++q1) smem[q1 * C64_BUF + n1] = b[q1];
         }
-        bfly4<true>(b[0], b[1], b[2], b[3]);                                // b[q1] = sum_m' conj(w4)^(q1 m') b[m']
-        if (c != 0) {
-#pragma unroll
-            for (int q1 = 0; q1 < 4; ++q1) b[q1] = cmulc(b[q1], kW64[((4 * q1 + i) * c) & 63]);
-        }
-#pragma unroll
-        for (int q1 = 0; q1 < 4; ++q1) smem[q1 * C64_BUF + n1] = b[q1];
     }
     cluster.sync();
 
     // ---- phase F: CTA k combines n1 in [1024 k, 1024 k + 1024): radix-4 over the CTAs through distributed shared memory
     {
-        const int n1 = C64_TPB * c + tau;
         const float2* __restrict__ peer[C64_CL];
 #pragma unroll
         for (int cc = 0; cc < C64_CL; ++cc) peer[cc] = cluster.map_shared_rank(smem, cc);
         constexpr float scale = 1.0f / (float)C64_M;
-        float2 val[4][4];
+#pragma unroll 1
+        for (int vt = 0; vt < NV; ++vt) {
+            const int n1 = C64_TPB * c + threadIdx.x + vt * NT;
+            float2 val[4][4];
 #pragma unroll
-        for (int q1 = 0; q1 < 4; ++q1)
+            for (int q1 = 0; q1 < 4; ++q1)
 #pragma unroll
-            for (int cc = 0; cc < C64_CL; ++cc) val[q1][cc] = peer[cc][q1 * C64_BUF + n1];
+                for (int cc = 0; cc < C64_CL; ++cc) val[q1][cc] = peer[cc][q1 * C64_BUF + n1];
 #pragma unroll
-        for (int q1 = 0; q1 < 4; ++q1) {
-            bfly4<true>(val[q1][0], val[q1][1], val[q1][2], val[q1][3]);    // val[q1][q2] = sum_c conj(w4)^(q2 c) v_c
+            for (int q1 = 0; q1 < 4; ++q1) {
+                bfly4<true>(val[q1][0], val[q1][1], val[q1][2], val[q1][3]);    // val[q1][q2] = sum_c conj(w4)^(q2 c) v_c
 #pragma unroll
-            for (int q2 = 0; q2 < 4; ++q2) {
-                const int mo = n1 + C64_NS * (q1 + 4 * q2) - D;             // output sample index
-                if (mo >= 0 && mo < sr) {
-                    const bool ok = mo < nvalid;
-                    wl[mo] = ok ? val[q1][q2].x * scale : 0.f;
-                    wr[mo] = ok ? val[q1][q2].y * scale : 0.f;
+                for (int q2 = 0; q2 < 4; ++q2) {
+                    const int mo = n1 + C64_NS * (q1 + 4 * q2) - D;             // output sample index
+                    if (mo >= 0 && mo < sr) {
+                        const bool ok = mo < nvalid;
+                        wl[mo] = ok ? val[q1][q2].x * scale : 0.f;
+                        wr[mo] = ok ? val[q1][q2].y * scale : 0.f;
+                    }
                 }
             }
         }

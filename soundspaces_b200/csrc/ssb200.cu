@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -55,6 +56,7 @@ struct ssb_ctx {
     int sm_count;
     float2* tw[16];      // twiddle tables by log2n (device)
     float2* twm64;       // single-block plan: TWM[r][tau] = w_65536^(tau r), r < 16, tau < 1024
+    int c64_groups;      // single-block plan: 256-thread groups per CTA (2 or 4)
     float* window;       // 512-float centre-padded periodic Hann(400)
     int64_t launches;
     // optional per-kernel CUDA-event timing (bench.py roofline); see ssb_set_kernel_timing
@@ -1093,7 +1095,14 @@ static int create_impl(ssb_ctx* ctx, int device) {
             }
         SSB_CUDA(ctx, cudaMalloc(&ctx->twm64, twm.size() * sizeof(float2)));
         SSB_CUDA(ctx, cudaMemcpy(ctx->twm64, twm.data(), twm.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        SSB_CUDA(ctx, cudaFuncSetAttribute(conv64k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C64_SMEM_BYTES));
+        SSB_CUDA(ctx, cudaFuncSetAttribute(conv64k_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, C64_SMEM_BYTES));
+        SSB_CUDA(ctx, cudaFuncSetAttribute(conv64k_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C64_SMEM_BYTES));
+        // groups of 256 threads per CTA of the single-block kernel: 4 (default) takes the whole SM; 2 leaves half of the
+        // SM's registers and warp slots to co-resident kernels of other streams.  Measured (profiles/times_r02b_block64_groups.log):
+        // the kernel takes the SAME time with half the threads (96.8 vs 92.8 us per 128 envs) -- it is bound by the chain of
+        // phases of the ~33 envs in flight, not by warps -- and the freed half of the SM did not buy overlap (121.7 vs 119.4 us per step)
+        const char* g = getenv("SSB200_C64_GROUPS");
+        ctx->c64_groups = (g && g[0] == '2') ? 2 : 4;
     }
     if (setup_smem_attrs<12>() || setup_smem_attrs<13>() || setup_smem_attrs<14>())
         SSB_FAIL(ctx, SSB_E_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s",
@@ -1333,8 +1342,12 @@ static cudaError_t launch_conv_any(ssb_ctx* ctx, const ssb_plan* plan, int B, co
                                    cudaStream_t st) {
     if (plan->log2n == C64_LOG2M) {
         LaunchTimer lt(ctx, K_CONV64K, st);
-        conv64k_kernel<<<C64_CL * B, C64_TPB, C64_SMEM_BYTES, st>>>(d_reqs, (const float2*)d_rir_bank, (const float2*)d_xpool,
-                                                                     d_wave, (long long)wave_stride, plan->sr, ctx->tw[12], ctx->twm64);
+        if (ctx->c64_groups == 2)
+            conv64k_kernel<2><<<C64_CL * B, 512, C64_SMEM_BYTES, st>>>(d_reqs, (const float2*)d_rir_bank, (const float2*)d_xpool,
+                                                                        d_wave, (long long)wave_stride, plan->sr, ctx->tw[12], ctx->twm64);
+        else
+            conv64k_kernel<4><<<C64_CL * B, 1024, C64_SMEM_BYTES, st>>>(d_reqs, (const float2*)d_rir_bank, (const float2*)d_xpool,
+                                                                         d_wave, (long long)wave_stride, plan->sr, ctx->tw[12], ctx->twm64);
         return cudaGetLastError();
     }
     switch (plan->log2n) {
