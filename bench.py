@@ -274,27 +274,20 @@ def numa_bind(local_rank, torch):
         return "not bound: " + repr(e)[:80]
 
 
-# per-step LIVE traffic of the whole path: `ncu --replay-mode range --cache-control none` around one steady-state step
-# of this workload (both internal streams running concurrently, caches as the previous steps left them); committed captures
-LIVE_TRAFFIC = {
-    "partitioned": {"dram_bytes": 17839616 + 162457088, "l2_bytes": 661364256, "source": "profiles/live_traffic_r02_base_1step.csv"},
-    "block64": None,   # filled in from profiles/live_traffic_r02_block64_1step.csv once captured (see LIVE_TRAFFIC_BLOCK64)
-}
-LIVE_TRAFFIC_BLOCK64 = os.path.join(ROOT, "profiles", "live_traffic_r02_block64_1step.csv")
-# FMA-pipe cycles per SM and executed warp-instructions per launch from committed `ncu --set full` captures, by kernel
-# (64-env launches of the C2 workload): the compute roofline this FP32 path really has
+# LIVE figures of one step of the C2 workload, per convolution plan, from the committed range captures (scratch/prof_final.sh:
+# `ncu --replay-mode range --cache-control none` around 4 consecutive steady-state steps, both internal streams running
+# concurrently, caches as the previous steps left them): DRAM / L2 bytes and the time the FMA pipes / issue slots were busy
+LIVE_STEP = os.path.join(ROOT, "profiles", "live_step_r02b.json")
+# FMA-pipe cycles per SM and executed warp-instructions per launch from the committed `ncu --set full` captures, by kernel
+# (64-env launches of the C2 workload): the per-kernel view of the same thing
 NCU_PER_LAUNCH = os.path.join(ROOT, "profiles", "ncu_per_launch.json")
 
 
-def read_live_traffic(path):
+def read_live_step(path_name):
     try:
-        vals = {}
-        for line in open(path):
-            p = [x.strip('"') for x in line.strip().split('","')]
-            if len(p) > 3 and p[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum"):
-                vals[p[-3]] = float(p[-1].replace(",", "").strip('"'))
-        return {"dram_bytes": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"], "l2_bytes": vals.get("lts__t_bytes.sum"),
-                "source": os.path.relpath(path, ROOT)}
+        d = json.load(open(LIVE_STEP))[path_name]
+        return {"dram_bytes": d["dram_bytes_per_step"], "l2_bytes": d["l2_bytes_per_step"], "fma_busy_us": d["fma_pipe_busy_us_per_step"],
+                "issue_busy_us": d["issue_busy_us_per_step"], "source": d["source"]}
     except Exception:
         return None
 
@@ -518,11 +511,12 @@ def run_gpu(args, rank, local_rank, world):
             r2.ctx.set_kernel_timing(False)
             step(0); step2(0)
             torch.cuda.synchronize()
-            live2 = (read_live_traffic(LIVE_TRAFFIC_BLOCK64) if other == "block64" else LIVE_TRAFFIC["partitioned"])
+            live2 = read_live_step(other)
             alt = {"plan": other, "value": B * args.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps, "repeats": reps2,
                    "kernel_ms_all": {k: v[0] / args.steps for k, v in kt2.items() if v[1]},
                    "traffic": live2["dram_bytes"] if live2 else None, "traffic_source": live2["source"] if live2 else None,
                    "traffic_over_algorithmic": (live2["dram_bytes"] / (ALG_BYTES_PER_FRAME * B)) if live2 else None,
+                   "fma_pipe_frac_live": (live2["fma_busy_us"] / (ms2 / args.steps * 1e3)) if live2 else None,
                    "max_abs_diff_vs_headline_plan": float((out2 - spec_out).abs().max())}
             del r2, b2
         except Exception as e:          # noqa: BLE001
@@ -551,7 +545,7 @@ def run_gpu(args, rank, local_rank, world):
         achieved = alg_bytes_launch / (dom_ms * 1e-3) / 1e9
         step_ms = ms_max / args.steps
         kernel_sum = sum(per_step_ms.values())
-        live = (read_live_traffic(LIVE_TRAFFIC_BLOCK64) if path == "block64" else None) or (LIVE_TRAFFIC[path] if path == "partitioned" else None)
+        live = read_live_step(path)
         # compute roofline of the kernels as built: the time the FMA pipes / the issue slots need for one step's
         # instructions (counts per launch from the committed ncu capture) over the measured step time
         fma_frac = issue_frac = None
@@ -579,9 +573,8 @@ def run_gpu(args, rank, local_rank, world):
                 "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": live["dram_bytes"] if live else None,
-                "traffic_source": (live["source"] + ": dram__bytes_read.sum + dram__bytes_write.sum of ONE LIVE STEP of this workload "
-                                   "(all kernels of the step, ncu range replay without cache control), to be read against "
-                                   "algorithmic_bytes_per_step") if live else None,
+                "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum per LIVE STEP of this workload (all kernels of the step; to be "
+                                   "read against algorithmic_bytes_per_step): " + live["source"]) if live else None,
                 "traffic_over_algorithmic": (live["dram_bytes"] / alg_bytes_launch) if live else None,
                 "l2_bytes_per_step": live.get("l2_bytes") if live else None,
                 "peak_source": peak_src,
@@ -596,6 +589,10 @@ def run_gpu(args, rank, local_rank, world):
                 "fp32_lane_op_peak_measured": "36.6e12 FP32-pipe lane-ops/s (FADD2 / FFMA2 issue rate, profiles/f32x2_bench_r02.log): an "
                                               "add-dominated FFT can at most reach 36.6 TFLOP/s, not the 73 TFLOP/s of pure FMA code",
                 "fma_pipe_frac": fma_frac, "issue_slot_frac": issue_frac,
+                "fma_pipe_frac_live": (live["fma_busy_us"] / (step_ms * 1e3)) if live else None,
+                "issue_slot_frac_live": (live["issue_busy_us"] / (step_ms * 1e3)) if live else None,
+                "fma_pipe_note": "fma_pipe_frac: per-launch FMA-pipe cycles of the committed per-kernel captures x launches per step / this run's step time; "
+                                 "fma_pipe_frac_live: FMA-pipe busy time per step measured over a live range of 4 steps / this run's step time",
                 "note": "FFT work is FP32-pipe bound (about 100 flop/B at algorithmic traffic): fma_pipe_frac / issue_slot_frac are the "
                         "fractions that measure kernel quality; see DESIGN.md",
             },

@@ -236,8 +236,11 @@ fwd_src_kernel(const float* __restrict__ src, int S, long long m0, int wrap, int
 // touches of the same slot column are L1 hits.  grid (N / 256, B); block 256.
 // ---------------------------------------------------------------------------
 #ifndef MACB_PREFETCH
-#define MACB_PREFETCH 0          // 0: all source windows loaded up front (measured default)
+#define MACB_PREFETCH 0          // 0: all source windows loaded up front (measured default; 3 / 4 / 6 slower, profiles/ab_r02_prepared.log)
 #endif
+// Also measured and dropped (profiles/ab_r02_macb_envs.log): one CTA looping over 2 / 4 / 8 envs with the source windows kept
+// in registers (X crosses the L2->SM link once per group instead of once per env): 0.0902 / 0.0926 / 0.1007 ms per step against
+// 0.0902 -- the smaller grid costs more than the saved L2 traffic gains.
 #ifdef MACB_MIN_BLOCKS
 #define MACB_BOUNDS __launch_bounds__(256, MACB_MIN_BLOCKS)
 #else
