@@ -740,10 +740,57 @@ def extra_workloads(args, dev, torch, barrier):
     except Exception as e:          # noqa: BLE001
         res["C4_error"] = repr(e)[:200]
     try:
+        res["C1_single_env"] = c1_single_env(dev, torch)
+    except Exception as e:          # noqa: BLE001
+        res["C1_error"] = repr(e)[:200]
+    try:
         res["C5_rollout"] = c5_rollout(dev, torch)
     except Exception as e:          # noqa: BLE001
         res["C5_error"] = repr(e)[:200]
     return res
+
+
+def c1_single_env(dev, torch, sr=44100, taps=22050, reps=200):
+    """BASELINE.json configs[0]: ONE env, 1-s clip at 44.1 kHz x 22050-tap binaural RIR read from a wav file on
+    disk, through the reference's own per-env call: sim.get_current_spectrogram_observation(compute_spectrogram) -> host
+    ndarray (compat mode: one render + blocking read-back per call; memo defeated by alternating two receiver nodes whose
+    dict entries are dropped).  Latency per call next to the CPU port's time for the same frame on one core."""
+    import tempfile
+    from scipy.io import wavfile
+    from soundspaces_b200.replay import ReplayScene, ReplaySim
+    from soundspaces_b200.sensors import SpectrogramSensor
+    from soundspaces_b200.simulator import AudioRenderService
+    from oracle import audio_oracle as ao
+    from synth import make_rir, make_source
+    svc = AudioRenderService(sr, device=dev, max_taps=sr, n_terms=1)
+    clip = make_source(3, sr)
+    with tempfile.TemporaryDirectory() as d:
+        scene = ReplayScene("apartment_0", side=2, rir_root=d)
+        rirs = [make_rir(900 + i, taps) for i in range(2)]
+        for i in range(2):
+            os.makedirs(os.path.join(scene.rir_dir, "0"), exist_ok=True)
+            wavfile.write(os.path.join(scene.rir_dir, "0", f"{i}_3.wav"), sr, rirs[i])
+        sim = ReplaySim(svc, scene, "telephone.wav", clip, source_node=3, start_node=0, deferred=False)
+        sim.b200_prefetch = False
+        fn = SpectrogramSensor.compute_spectrogram
+        first = time.perf_counter()
+        spec = sim.get_current_spectrogram_observation(fn)              # cold: wav read + upload + source spectrum
+        cold_ms = (time.perf_counter() - first) * 1e3
+        t0 = time.perf_counter()
+        for i in range(reps):
+            sim._receiver_position_index = i & 1
+            sim._spectrogram_cache, sim._audiogoal_cache = {}, {}
+            spec = sim.get_current_spectrogram_observation(fn)
+        gpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+        t0 = time.perf_counter()
+        for i in range(5):
+            _, ref = ao.render_frame(clip, rirs[i & 1], sr)
+        cpu_ms = (time.perf_counter() - t0) * 1e3 / 5
+        ok = bool(np.allclose(spec, ao.render_frame(clip, rirs[(reps - 1) & 1], sr)[1], rtol=1e-4, atol=1e-5))
+    return {"value": 1e3 / gpu_ms, "unit": UNIT, "ms_per_call": gpu_ms, "first_call_ms": cold_ms, "cpu_port_ms_per_frame_one_core": cpu_ms,
+            "matches_oracle": ok,
+            "workload": "1 env, 44.1 kHz, 22050-tap RIR from a wav file, compat path: get_current_spectrogram_observation -> host ndarray "
+                        "(render B=1 + blocking device->host copy per call; RIR resident after the first read)"}
 
 
 def c5_rollout(dev, torch, n_envs=16, num_steps=150, sr=16000, taps=16000):
