@@ -717,7 +717,18 @@ def extra_workloads(args, dev, torch, barrier):
             r.logmel(r.convolve_prepared(valid[i & 1]), 64, 2, out=mel_out)
         run("C3_valid_logmel", logmel, Bc, 8 * 48000 + 4 * 63999 // 64 + 8 * 64 * 101, 13.2e6 + 101 * 2 * 2 * 2 * 257,
             f"as C3_valid with the log-mel head (64 Slaney mels, power 2; extension, parity unpinned) -> (64,101,2); {plan}")
-        del r, bank, banks
+        # the same two workloads on the single-block plan (48000 taps <= 65536 - 16000 + 1: one 65536-point kernel per env)
+        r64 = BatchedAudioRenderer(sr, L, device=dev, prefer_block64=True)
+        ids64 = r64.set_dense_rir_bank(bank)
+        t1, t4 = r64.add_source(make_source(1, sr)), r64.add_source(make_source(2, 4 * sr))
+        head64 = [r64.prepare([AudioRequest(rir=ids64[k * Bc + i], source=t1) for i in range(Bc)]) for k in range(2)]
+        valid64 = [r64.prepare([AudioRequest(rir=ids64[k * Bc + i], source=t4, offset=3 * sr) for i in range(Bc)]) for k in range(2)]
+        if head64[0].plan.log2n == 16:
+            run("C3_head_block64", lambda i: r64.execute(head64[i & 1], out=out), Bc, alg_bytes(16000, 16000, 64, sr), 7.4e6,
+                "C3_head on the single-block cluster kernel")
+            run("C3_valid_block64", lambda i: r64.execute(valid64[i & 1], out=out), Bc, alg_bytes(48000, 63999, 64, sr), 13.2e6,
+                "C3_valid on the single-block cluster kernel")
+        del r, r64, bank, banks
     except Exception as e:          # noqa: BLE001
         res["C3_error"] = repr(e)[:200]
     try:
