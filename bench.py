@@ -234,7 +234,7 @@ def run_reference(args, rank):
 MIN_REGION_S = 0.06          # timed regions shorter than this are repeated (median reported) until >= 0.05 s have been timed in all
 
 
-def timed_region(step, steps, barrier, torch, first_index=0):
+def timed_region(step, steps, barrier, torch, first_index=0, allmax=None):
     """CUDA-event time of exactly `steps` calls of step(i), barrier + synchronize on both sides.  When the region is
     shorter than MIN_REGION_S it is repeated (same K steps each time) and the MEDIAN is returned, so that a 20-step
     run of a 0.1 ms step is not a 2 ms sample.  Returns (ms of one K-step region, repeats, total timed seconds)."""
@@ -248,9 +248,12 @@ def timed_region(step, steps, barrier, torch, first_index=0):
         barrier()
         return e0.elapsed_time(e1)
     first = once()
+    # every rank must repeat the region the SAME number of times (each repetition contains barriers): the count is
+    # decided on the slowest rank's first measurement, never on the local one (a rank-local count deadlocks at N > 1)
+    ref = allmax(first) if allmax is not None else first
     reps = 1
-    if first * 1e-3 < MIN_REGION_S:
-        reps = int(min(400, max(3, np.ceil(MIN_REGION_S / max(first * 1e-3, 1e-6)) + 1))) | 1      # odd
+    if ref * 1e-3 < MIN_REGION_S:
+        reps = int(min(400, max(3, np.ceil(MIN_REGION_S / max(ref * 1e-3, 1e-6)) + 1))) | 1      # odd
     times = [first] + [once() for _ in range(reps - 1)]
     return float(np.median(times)), reps, float(np.sum(times)) * 1e-3
 
@@ -313,7 +316,9 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective that some rank never reaches must not hang the box: abort after 3 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     B = ENVS_PER_GPU
     r = BatchedAudioRenderer(SR, TAPS, device=dev, log2n=args.log2n, prefer_block64=(args.plan == "block64"))
@@ -339,6 +344,16 @@ def run_gpu(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def agree(ok):
+        """True only when EVERY rank succeeded.  The optional legs below set up rank-locally inside try / except and
+        call this before their first collective, so that a rank that failed (out of pinned memory, ...) cannot leave
+        the others waiting in a barrier."""
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() == 1.0)
+
     def step(i):
         r.execute(batches[i % N_BANKS], out=spec_out)
 
@@ -352,7 +367,7 @@ def run_gpu(args, rank, local_rank, world):
         time.sleep(0.25)
     launches0 = r.ctx.launch_count
     t_wall0 = time.time()
-    ms, reps, region_s = timed_region(step, args.steps, barrier, torch)
+    ms, reps, region_s = timed_region(step, args.steps, barrier, torch, allmax=allmax)
     t_wall1 = time.time()
     launches = (r.ctx.launch_count - launches0) // reps
     # a long enough region for the clock sampler: keep the GPU under the same load for >= 1.5 s
@@ -372,6 +387,7 @@ def run_gpu(args, rank, local_rank, world):
     # batch; the spectrogram kernel writes straight into this rank's slice of the gather buffer
     gather_info = None
     if world > 1 and not args.no_gather:
+        err = None
         try:
             from soundspaces_b200.distributed import GatheredObservations
             gobs = GatheredObservations(B * world, r.spec_shape, rank, world, dev)
@@ -381,10 +397,15 @@ def run_gpu(args, rank, local_rank, world):
             def gstep(i):
                 r.execute(batches[i % N_BANKS], out=gobs.local)
                 state["flat"] = gobs.gather()
-
+        except Exception as e:          # noqa: BLE001
+            err = repr(e)[:200]
+        if not agree(err is None):
+            gather_info = {"error": err or "set-up failed on another rank"}
+    if world > 1 and not args.no_gather and gather_info is None:
+        try:
             for i in range(max(3, args.warmup // 2)):
                 gstep(i)
-            gms, greps, _ = timed_region(gstep, args.steps, barrier, torch)
+            gms, greps, _ = timed_region(gstep, args.steps, barrier, torch, allmax=allmax)
             gms = allmax(gms)
             # every rank must now hold every rank's rows: compare a checksum of the gathered batch across ranks,
             # and this rank's own rows with what it rendered without the collective
@@ -419,7 +440,7 @@ def run_gpu(args, rank, local_rank, world):
     hs.set_requests(sid, silent=sil)
     for _ in range(max(3, args.warmup // 4)):
         hs.run()
-    e2e_ms, _, _ = timed_region(lambda i: hs.run(), args.steps, barrier, torch)
+    e2e_ms, _, _ = timed_region(lambda i: hs.run(), args.steps, barrier, torch, allmax=allmax)
     e2e_ms_max = allmax(e2e_ms)
     checksum = float(hs.h_spec.double().sum())
     hs_bytes = (hs.h2d_bytes, hs.d2h_bytes)
@@ -427,6 +448,7 @@ def run_gpu(args, rank, local_rank, world):
     # ---- end to end with a device-resident RIR bank and a stated miss rate (what training does once the
     # scene's working set is resident: per step only the MISSING RIRs cross PCIe, the spectrograms come back)
     miss_info = None
+    err = None
     try:
         miss = args.miss_rate
         n_miss = max(1, int(round(miss * B)))
@@ -464,7 +486,15 @@ def run_gpu(args, rank, local_rank, world):
 
         for i in range(6):
             mstep(i)
-        mms, _, _ = timed_region(mstep, args.steps, mbarrier, torch)
+        torch.cuda.synchronize()
+    except Exception as e:          # noqa: BLE001
+        err = repr(e)[:200]
+    if not agree(err is None):
+        miss_info = {"error": err or "set-up failed on another rank"}
+    try:
+        if miss_info is not None:
+            raise RuntimeError(miss_info["error"])
+        mms, _, _ = timed_region(mstep, args.steps, mbarrier, torch, allmax=allmax)
         mms = allmax(mms)
         miss_info = {"value": B * world * args.steps / (mms * 1e-3), "unit": UNIT, "ms_per_step": mms / args.steps,
                      "miss_rate": n_miss / B, "h2d_bytes_per_step": int(n_miss * TAPS * 8),
@@ -479,29 +509,34 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- the public API paths: per step host work included
     api_info = {}
+    err = None
     try:
         def api_step(i):                                            # render(list[AudioRequest]): prepare() every step
             r.execute(r.prepare(req_lists[i % N_BANKS]), out=spec_out)
         for i in range(5):
             api_step(i)
-        ams, _, _ = timed_region(api_step, args.steps, barrier, torch)
         rir_arr = [np.asarray(ids[k * B:(k + 1) * B], dtype=np.int64) for k in range(N_BANKS)]
 
         def arr_step(i):                                            # prepare_arrays(): requests held as arrays
             r.execute(r.prepare_arrays(rir_arr[i % N_BANKS], sid, silent=sil), out=spec_out)
         for i in range(5):
             arr_step(i)
-        bms, _, _ = timed_region(arr_step, args.steps, barrier, torch)
+        torch.cuda.synchronize()
+    except Exception as e:          # noqa: BLE001
+        err = repr(e)[:200]
+    ok_api = agree(err is None)
+    try:
+        if not ok_api:
+            raise RuntimeError(err or "set-up failed on another rank")
+        ams, _, _ = timed_region(api_step, args.steps, barrier, torch, allmax=allmax)
+        bms, _, _ = timed_region(arr_step, args.steps, barrier, torch, allmax=allmax)
         api_info = {"api_path": {"value": B * world * args.steps / (allmax(ams) * 1e-3), "unit": UNIT,
                                  "what": "execute(prepare(list[AudioRequest])) every step: request resolution + H2D of the request array + launches"},
                     "api_path_arrays": {"value": B * world * args.steps / (allmax(bms) * 1e-3), "unit": UNIT,
                                         "what": "execute(prepare_arrays(...)) every step: requests held as numpy columns"}}
     except Exception as e:          # noqa: BLE001
         api_info = {"api_path": {"error": repr(e)[:200]}}
-    try:
-        api_info["plugin_path"] = plugin_path_leg(args, r, bank_host, sid, dev, world, barrier, allmax, torch)
-    except Exception as e:          # noqa: BLE001
-        api_info["plugin_path"] = {"error": repr(e)[:200]}
+    api_info["plugin_path"] = plugin_path_leg(args, r, bank_host, sid, dev, world, barrier, allmax, agree, torch)
 
     # ---- the other convolution plan on the same workload (N = 1): the single-block cluster kernel trades step time
     # for DRAM traffic (no H / Y intermediates); reported next to the headline, which uses the faster plan
@@ -639,9 +674,28 @@ def run_gpu(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def plugin_path_leg(args, r, bank_host, sid, dev, world, barrier, allmax, torch):
+def plugin_path_leg(args, r, bank_host, sid, dev, world, barrier, allmax, agree, torch):
     """Frames/s through the per-env plugin surface: SpectrogramSensor.get_observation per env (deferred handles) +
     batch_obs, every env at a NEW grid node every step (100 % memo miss, resident RIRs)."""
+    err = None
+    try:
+        pstep = _plugin_setup(args, r, bank_host, sid, dev, torch)
+        for i in range(5):
+            pstep(i)
+        torch.cuda.synchronize()
+    except Exception as e:          # noqa: BLE001
+        err = repr(e)[:200]
+    if not agree(err is None):
+        return {"error": err or "set-up failed on another rank"}
+    B = ENVS_PER_GPU
+    pms, _, _ = timed_region(pstep, args.steps, barrier, torch, allmax=allmax)
+    pms = allmax(pms)
+    return {"value": B * world * args.steps / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms / args.steps,
+            "what": "per env: SpectrogramSensor.get_observation -> DeferredObservation handle; per step: batch_obs -> ONE render into "
+                    "the rollout slot (128 envs, every env at a new node each step, RIRs resident)"}
+
+
+def _plugin_setup(args, r, bank_host, sid, dev, torch):
     from soundspaces_b200.replay import ReplayScene, ReplaySim, ReplayVectorEnv
     from soundspaces_b200.sensors import batch_obs
     from soundspaces_b200.simulator import AudioRenderService
@@ -667,13 +721,7 @@ def plugin_path_leg(args, r, bank_host, sid, dev, world, barrier, allmax, torch)
             s._spectrogram_cache = {}
         batch_obs(envs.observe(), device=dev, out=out)
 
-    for i in range(5):
-        pstep(i)
-    pms, _, _ = timed_region(pstep, args.steps, barrier, torch)
-    pms = allmax(pms)
-    return {"value": B * world * args.steps / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms / args.steps,
-            "what": "per env: SpectrogramSensor.get_observation -> DeferredObservation handle; per step: batch_obs -> ONE render into "
-                    "the rollout slot (128 envs, every env at a new node each step, RIRs resident)"}
+    return pstep
 
 
 def extra_workloads(args, dev, torch, barrier):

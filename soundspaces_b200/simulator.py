@@ -266,19 +266,22 @@ class B200AudioMixin:
                 pass
         svc.prefetch(keys)
 
-    def _b200_request(self) -> AudioRequest:
+    def _b200_request(self, az=None) -> AudioRequest:
         """The request equivalent to one call of ``_compute_audiogoal`` (simulator.py:608-666),
-        including the ``_audio_index`` advance at :635."""
-        svc = self._b200_service()
-        sr = self.config.AUDIO.RIR_SAMPLING_RATE
+        including the ``_audio_index`` advance at :635.  ``az``: the azimuth when the caller has already read it."""
+        svc = getattr(self, "_b200_svc", None) or self._b200_service()
+        cfg = self.config
+        sr = cfg.AUDIO.RIR_SAMPLING_RATE
         if self._episode_step_count > self._duration:
             return AudioRequest(rir=-1, source=0, silent=True)
         rid, inline = -1, None
-        if not self.config.USE_RENDERED_OBSERVATIONS:
+        if not cfg.USE_RENDERED_OBSERVATIONS:
             # simulator.py:626: RIR rendered by habitat-sim for this step -> transient, supplied inline
             inline = np.transpose(np.array(self._sim.get_sensor_observations()["audio_sensor"]))
         else:
-            rir_dir, az, recv = self.binaural_rir_dir, self.azimuth_angle, self._receiver_position_index
+            rir_dir, recv = self.binaural_rir_dir, self._receiver_position_index
+            if az is None:
+                az = self.azimuth_angle
             rid = svc.rir((rir_dir, az, recv, self._source_position_index))
             if self.b200_prefetch:
                 self._b200_prefetch_next(svc, rir_dir, az, recv, self._source_position_index)
@@ -290,7 +293,7 @@ class B200AudioMixin:
             self._audio_index = (self._audio_index + 1) % self._audio_length
             offset = index * sr
         req = AudioRequest(rir=rid, source=sid, offset=offset, rir_array=inline)
-        if self.config.AUDIO.HAS_DISTRACTOR_SOUND:
+        if cfg.AUDIO.HAS_DISTRACTOR_SOUND:
             dclip = self._source_sound_dict[self._current_distractor_sound]
             req.distractor_source = svc.source(self._current_distractor_sound, dclip)
             req.distractor_rir = svc.rir((self.binaural_rir_dir, self.azimuth_angle, self._receiver_position_index,
@@ -371,13 +374,14 @@ class B200AudioMixin:
         """Deferred mode: enqueue, return the handle.  The memo is the reference's own ``_spectrogram_cache`` dict
         (keyed ``(source, receiver, azimuth)``, simulator.py:696-699), which the reference REPLACES on every scene
         or sound change (simulator.py:395-397) -- so a handle can never outlive its scene."""
-        batcher = self._b200_service().batcher
+        svc = getattr(self, "_b200_svc", None) or self._b200_service()
         if self.config.AUDIO.HAS_DISTRACTOR_SOUND:
-            return batcher.enqueue(self._b200_request())
-        joint_index = (self._source_position_index, self._receiver_position_index, self.azimuth_angle)
+            return svc.batcher.enqueue(self._b200_request())
+        az = self.azimuth_angle
+        joint_index = (self._source_position_index, self._receiver_position_index, az)
         handle = self._spectrogram_cache.get(joint_index)
         if handle is None:
-            handle = self._spectrogram_cache[joint_index] = batcher.enqueue(self._b200_request())
+            handle = self._spectrogram_cache[joint_index] = svc.batcher.enqueue(self._b200_request(az))
         return handle
 
     def get_current_spectrogram_observation(self, audiogoal2spectrogram):
