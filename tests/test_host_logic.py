@@ -269,3 +269,50 @@ def test_prepare_arrays_equals_prepare():
                                 distractor_source=None if dsrc[i] < 0 else int(dsrc[i])) for i in range(8)])
     assert a.n == 8 and a.reqs_host.tobytes() == b.reqs_host.tobytes()
     assert r.prepare_arrays(np.arange(3), 0, out_samples=4000).reqs_host["out_samples"].tolist() == [4000] * 3
+
+
+# ---------------------------------------------------------------------------------- bench.py timed_region across ranks
+def _timed_region_worker(rank, world, port, tmp):
+    """Two gloo ranks whose local first measurement falls on different sides of the repeat threshold: the repeat count
+    (every repetition contains barriers) must still be the same on both, or the run deadlocks."""
+    import time
+    import types
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class FakeEvent:
+        def __init__(self, enable_timing=True):
+            self.t = None
+
+        def record(self):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+    fake_torch = types.SimpleNamespace(cuda=types.SimpleNamespace(Event=FakeEvent))
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    bench.MIN_REGION_S = 0.02
+    calls = []
+
+    def step(i):
+        calls.append(i)
+        time.sleep(0.0015 if rank == 0 else 0.0004)          # rank 0: 15 ms per region, rank 1: 4 ms: different local repeat counts
+    ms, reps, total = bench.timed_region(step, 10, dist.barrier, fake_torch, allmax=allmax)
+    open(os.path.join(tmp, f"reps{rank}"), "w").write(str(reps))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_timed_region_repeat_count_is_rank_consistent(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29300 + os.getpid() % 300
+    mp.spawn(_timed_region_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (int(open(tmp_path / f"reps{k}").read()) for k in (0, 1))
+    assert r0 == r1 and r0 >= 3
