@@ -143,7 +143,12 @@ struct LaunchTimer {          // records an event pair around one kernel launch 
     ~LaunchTimer() {
         if (!on) return;
         cudaEventRecord(tl.b, st);
-        ctx->timed->push_back(tl);
+        try {                                     // a destructor must not throw (std::terminate): drop the sample instead
+            ctx->timed->push_back(tl);
+        } catch (...) {
+            cudaEventDestroy(tl.a);
+            cudaEventDestroy(tl.b);
+        }
     }
 };
 
