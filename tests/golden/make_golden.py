@@ -53,6 +53,15 @@ CONTINUOUS_CASES = {
 }
 
 
+# round 2: the continuous simulator's EARLY branch with a window that runs past the end of the clip
+# (continuous_simulator.py:433-437: the clip is NOT wrapped there -- zeros past its end); kept in a second file so that the
+# round-1 fixture stays byte-identical
+CONTINUOUS_EDGE_CASES = {
+    "a7_early_past_clip_end": dict(sr=16000, S=15000, L=14000, seed=26, sample_index=12000),
+    "a7_early_past_clip_end_crossfade": dict(sr=16000, S=15000, L=14000, seed=27, sample_index=12000, last_seed=270, last_L=5000),
+}
+
+
 def discrete_inputs(c):
     src = make_source(c["seed"], c["S"])
     rir = make_rir(c["seed"], c["L"]) if c["L"] > 0 else None
@@ -149,6 +158,19 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
     np.savez_compressed(path, **packed)
     print("wrote", path, os.path.getsize(path), "bytes,", len(packed), "arrays")
+
+    edge = {}
+    ref = rh.load_reference("reflect")
+    spec_fn = ref["nav"].SpectrogramSensor.compute_spectrogram
+    for name, c in CONTINUOUS_EDGE_CASES.items():
+        src, rir, last = continuous_inputs(c)
+        sim = rh.make_continuous_sim(ref, c["sr"], src, rir, sample_index=c["sample_index"], last_rir=last,
+                                     crossfade=last is not None)
+        edge[f"{name}/wave"] = sim.get_current_audiogoal_observation()
+        edge[f"{name}/spec_reflect"] = sim.get_current_spectrogram_observation(spec_fn)
+    path2 = os.path.join(ROOT, "tests", "golden", "reference_golden_r2.npz")
+    np.savez_compressed(path2, **edge)
+    print("wrote", path2, os.path.getsize(path2), "bytes,", len(edge), "arrays")
 
 
 if __name__ == "__main__":
