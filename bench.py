@@ -872,7 +872,7 @@ def c5_rollout(dev, torch, n_envs=16, num_steps=150, sr=16000, taps=16000):
     policy = AudioPolicy(svc.renderer.spec_shape).to(dev)
     storage = torch.zeros((num_steps + 1, n_envs) + svc.renderer.spec_shape, device=dev)
     trace = rng.choice([1, 1, 1, 2, 3], size=(num_steps, n_envs))              # recorded action trace (no STOP)
-    collect_rollout(envs, policy, storage, 20, trace[:20])                     # warm-up
+    collect_rollout(envs, policy, storage, min(20, num_steps), trace[:min(20, num_steps)])   # warm-up
     l0, f0 = svc.renderer.ctx.launch_count, svc.batcher.flushes
     t0 = time.time()
     pth, env_t, n = collect_rollout(envs, policy, storage, num_steps, trace)
