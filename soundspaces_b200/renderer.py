@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .planning import effective_taps, window_layout
+from .planning import window_layout
 from ._lib import PAD_MODES, REQ_DTYPE, SSB_FLAG_SILENT
 
 N_FFT, HOP, WIN, POOL, SPEC_ROWS = 512, 160, 400, 4, 65

@@ -16,7 +16,6 @@ protocol is used (habitat is not installable in the build image).
 """
 from __future__ import annotations
 
-from collections import defaultdict
 from typing import Any, Dict, List, Optional
 
 import numpy as np

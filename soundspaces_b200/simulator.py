@@ -31,7 +31,6 @@ from __future__ import annotations
 
 import logging
 import os
-import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Dict, Optional
 
@@ -97,7 +96,6 @@ class AudioRenderService:
         self._clock = 0                               # use counter behind the LRU order
         self._pool = ThreadPoolExecutor(max_workers=prefetch_workers, thread_name_prefix="ssb-rir") if prefetch_workers else None
         self._inflight: Dict[object, object] = {}    # key -> Future of _read_rir_file
-        self._lock = threading.Lock()
         self._batcher = None
         self.stats = {"hits": 0, "misses": 0, "prefetched": 0, "waited": 0, "compactions": 0}
 
