@@ -875,14 +875,15 @@ def c5_rollout(dev, torch, n_envs=16, num_steps=150, sr=16000, taps=16000):
     collect_rollout(envs, policy, storage, min(20, num_steps), trace[:min(20, num_steps)])   # warm-up
     l0, f0 = svc.renderer.ctx.launch_count, svc.batcher.flushes
     t0 = time.time()
-    pth, env_t, n = collect_rollout(envs, policy, storage, num_steps, trace)
+    pth, env_t, n = collect_rollout(envs, policy, storage, num_steps, trace, fused=True)
     wall = time.time() - t0
     rendered = sum(len(s._spectrogram_cache) for s in sims)
     return {"value": n / wall, "unit": "env-steps/s", "envs": n_envs, "num_steps": num_steps, "env_time_s": env_t, "pth_time_s": pth,
             "wall_s": wall, "renders": svc.batcher.flushes - f0, "kernel_launches": svc.renderer.ctx.launch_count - l0,
             "memo_entries": rendered, "rir_miss_rate": svc.miss_rate,
             "workload": "trace-replay env (8x8 grid scene, 16 kHz, 16000-tap RIRs resident) x SpectrogramSensor (deferred) x batch_obs into "
-                        "rollouts.observations['spectrogram'][step+1] x AudioCNN-shaped policy; ONE render per step for all envs"}
+                        "rollouts.observations['spectrogram'][step+1] x AudioCNN-shaped policy (first layer: the fused permute + Conv2d + ReLU "
+                        "kernel, SURVEY N2); ONE render per step for all envs"}
 
 
 def main():

@@ -216,19 +216,20 @@ class AudioPolicy(nn.Module):
 
 
 def collect_rollout(envs: ReplayVectorEnv, policy: AudioPolicy, storage: torch.Tensor, num_steps: int,
-                    forced_actions: Optional[np.ndarray] = None):
+                    forced_actions: Optional[np.ndarray] = None, fused: bool = False):
     """One rollout of ``num_steps`` env steps with the reference's timers (ppo_trainer.py:125-194): ``pth_time`` =
     action sampling + observation batching / insertion, ``env_time`` = ``envs.step``.  ``storage``: the
     ``(num_steps + 1, num_envs, 65, T', 2)`` tensor ``rollouts.observations["spectrogram"]``; the step's batch is
     rendered straight into ``storage[step + 1]`` by ``batch_obs`` (nothing for ``RolloutStorage.insert`` to copy).
-    ``forced_actions`` (``(num_steps, num_envs)``): replay a recorded action trace instead of the sampled actions."""
+    ``forced_actions`` (``(num_steps, num_envs)``): replay a recorded action trace instead of the sampled actions.
+    ``fused``: run the policy's first layer with the fused permute + Conv2d + ReLU kernel."""
     from .sensors import batch_obs
     dev = storage.device
     pth_time = env_time = 0.0
     batch_obs(envs.observe(), device=dev, out={"spectrogram": storage[0]})
     for step in range(num_steps):
         t0 = time.time()
-        _, actions, _ = policy.act(storage[step])
+        _, actions, _ = policy.act(storage[step], fused=fused)
         acts = actions.tolist() if forced_actions is None else forced_actions[step].tolist()
         pth_time += time.time() - t0
         t0 = time.time()
