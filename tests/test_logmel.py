@@ -1,7 +1,8 @@
 """Log-mel EXTENSION (BASELINE.json configs[2] names a log-mel front end; the reference has none).
 
 CPU: the oracle's librosa restatement (``oracle/audio_oracle.py::mel_filterbank`` / ``logmel``) is triangulated
-against torchaudio's independent Slaney filterbank and MelSpectrogram, and the filterbank the CUDA library builds
+against torchaudio's independent Slaney filterbank and MelSpectrogram and against ``transformers.audio_utils.mel_filter_bank``
+(a reimplementation of ``librosa.filters.mel``), and the filterbank the CUDA library builds
 (``ssb_mel_filterbank``, host only) is bit-identical to the restatement.  GPU: ``ssb_logmel_batch`` against the
 oracle, ``allclose(rtol=1e-4, atol=1e-5)`` -- the spectrogram tolerance of SURVEY.md 8(c)."""
 import numpy as np
@@ -25,6 +26,18 @@ def test_filterbank_restatement_vs_torchaudio(sr, n_mels):
     if n_mels <= 40:
         area = fb.sum(1) * (sr / 512.0)
         assert np.allclose(area[n_mels // 2:], 1.0, atol=0.05)
+
+
+@pytest.mark.parametrize("sr,n_mels", CASES)
+def test_filterbank_restatement_vs_transformers_audio_utils(sr, n_mels):
+    """A third, independent implementation: ``transformers.audio_utils.mel_filter_bank`` (written to reproduce
+    ``librosa.filters.mel``; float64 triangles) with Slaney scale + Slaney normalisation agrees to 1e-6 of peak."""
+    au = pytest.importorskip("transformers.audio_utils")
+    fb = ao.mel_filterbank(sr, 512, n_mels)
+    hf = au.mel_filter_bank(num_frequency_bins=257, num_mel_filters=n_mels, min_frequency=0.0, max_frequency=sr / 2.0,
+                            sampling_rate=sr, norm="slaney", mel_scale="slaney").T
+    assert hf.shape == fb.shape
+    assert np.abs(fb - hf).max() <= 1e-6 * np.abs(hf).max()
 
 
 @pytest.mark.parametrize("sr,n_mels", CASES)
